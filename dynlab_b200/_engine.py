@@ -1,0 +1,196 @@
+"""Host side of the C-ABI: device buffers (owned by torch), streams, transfers.
+
+PyTorch is plumbing here — it allocates device/pinned memory and provides the CUDA stream;
+every floating-point operation of the path happens inside ``libdynlab_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+_F64 = torch.float64
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "dynlab_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def as_coord(a) -> np.ndarray:
+    """Coordinate vector as contiguous float64 (numpy casts integer coordinates to float64
+    in np.gradient: numpy/lib/_function_base_impl.py:1242-1245)."""
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Engine:
+    """Per-device launcher.  Buffers that do not leave the engine (workspace, counters) are
+    cached; result tensors are allocated per call through torch's caching allocator."""
+
+    _by_device: dict[int, "Engine"] = {}
+
+    @classmethod
+    def get(cls, device=None) -> "Engine":
+        _require_cuda()
+        idx = torch.cuda.current_device() if device is None else torch.device(device).index
+        if idx is None:
+            idx = torch.cuda.current_device()
+        eng = cls._by_device.get(idx)
+        if eng is None:
+            eng = cls._by_device[idx] = Engine(idx)
+        return eng
+
+    def __init__(self, index: int):
+        self.device = torch.device("cuda", index)
+        self._workspace = None
+        self.counters = torch.zeros(nat.CNT_WORDS, dtype=torch.int64, device=self.device)
+
+    # -- plumbing ---------------------------------------------------------------------
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def workspace(self, xdim: int, ydim: int):
+        need = int(nat.lib.dlb_workspace_bytes(xdim, ydim))
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=self.device)
+        return self._workspace.data_ptr(), self._workspace.numel()
+
+    def empty(self, *shape, dtype=_F64):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def to_device(self, host: np.ndarray):
+        """Host float64 array -> device tensor (through pinned staging when large)."""
+        t = torch.from_numpy(np.ascontiguousarray(host, dtype=np.float64))
+        return t.to(self.device, non_blocking=False)
+
+    def to_host(self, t: torch.Tensor) -> np.ndarray:
+        """Device tensor -> numpy array backed by pinned host memory."""
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return h.numpy()
+
+    def read_counters(self) -> dict:
+        c = self.counters.cpu().numpy()
+        return {"nfev": int(c[nat.CNT_NFEV]), "accepted": int(c[nat.CNT_ACCEPTED]),
+                "rejected": int(c[nat.CNT_REJECTED]), "failed": int(c[nat.CNT_FAILED]),
+                "seeds": int(c[nat.CNT_SEEDS])}
+
+    # -- K1 ---------------------------------------------------------------------------
+    def flow_map(self, flow_id, params, x, y, row0, rows, t0, tf, rtol, atol,
+                 max_step=math.inf, first_step=0.0, out=None, nfev=None, status=None):
+        """Enqueue K1 for rows [row0, row0+rows) of the grid; returns the [rows, xdim, 2] tensor."""
+        xdim = len(x)
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = self.empty(rows, xdim, 2)
+            ws, wsz = self.workspace(xdim, max(len(y), rows))
+            p = nat.darray(params)
+            nat.check(nat.lib.dlb_flowmap_rk45(
+                flow_id, p, len(params), nat.dptr(x), xdim, nat.dptr(y), row0, rows,
+                float(t0), float(tf), float(rtol), float(atol), float(max_step), float(first_step),
+                out.data_ptr(), nfev.data_ptr() if nfev is not None else None,
+                status.data_ptr() if status is not None else None,
+                self.counters.data_ptr(), ws, wsz, self.stream()))
+        return out
+
+    def rk45_endpoints(self, flow_id, params, seeds, t0, tf, rtol, atol, max_step=math.inf,
+                       first_step=0.0, nfev=None, status=None):
+        m, n = seeds.shape
+        with torch.cuda.device(self.device):
+            out = self.empty(m, n)
+            ws, wsz = self.workspace(0, 0)
+            p = nat.darray(params)
+            a = nat.darray(np.broadcast_to(np.asarray(atol, dtype=np.float64), (n,)))
+            nat.check(nat.lib.dlb_rk45_endpoints(
+                flow_id, p, len(params), n, seeds.data_ptr(), m, float(t0), float(tf),
+                float(rtol), a, float(max_step), float(first_step), out.data_ptr(),
+                nfev.data_ptr() if nfev is not None else None,
+                status.data_ptr() if status is not None else None,
+                self.counters.data_ptr(), ws, wsz, self.stream()))
+        return out
+
+    # -- K2 ---------------------------------------------------------------------------
+    def ftle_stencil(self, fm_local, grow0, x, y, edge_order, t_span, out_row0, out_rows,
+                     xi_mode=nat.XI_NONE, out=None):
+        xdim, ydim = len(x), len(y)
+        nloc = fm_local.shape[0]
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = self.empty(out_rows, xdim)
+            xi = self.empty(out_rows, xdim, 2) if xi_mode != nat.XI_NONE else None
+            ws, wsz = self.workspace(xdim, ydim)
+            nat.check(nat.lib.dlb_ftle_stencil(
+                fm_local.data_ptr(), nloc, grow0, nat.dptr(x), xdim, nat.dptr(y), ydim,
+                int(edge_order), float(t_span), out_row0, out_rows, out.data_ptr(),
+                xi.data_ptr() if xi is not None else None, xi_mode, ws, wsz, self.stream()))
+        return out, xi
+
+    # -- K3 ---------------------------------------------------------------------------
+    def euler_stencil(self, mode, u_local, v_local, grow0, x, y, edge_order, out_row0, out_rows,
+                      negate=False, xi_mode=nat.XI_NONE):
+        xdim, ydim = len(x), len(y)
+        nloc = u_local.shape[0]
+        with torch.cuda.device(self.device):
+            out = self.empty(out_rows, xdim)
+            need_mask = mode in (nat.EULER_RATE, nat.EULER_RATIO)
+            mask = self.empty(out_rows, xdim, dtype=torch.uint8) if need_mask else None
+            xi = self.empty(out_rows, xdim, 2) if xi_mode != nat.XI_NONE else None
+            ws, wsz = self.workspace(xdim, ydim)
+            nat.check(nat.lib.dlb_euler_stencil(
+                mode, u_local.data_ptr(), v_local.data_ptr(), nloc, grow0, nat.dptr(x), xdim,
+                nat.dptr(y), ydim, int(edge_order), out_row0, out_rows, int(bool(negate)),
+                out.data_ptr(), mask.data_ptr() if mask is not None else None,
+                xi.data_ptr() if xi is not None else None, xi_mode, ws, wsz, self.stream()))
+        return out, mask, xi
+
+    # -- K0 ---------------------------------------------------------------------------
+    def flow_eval_grid(self, flow_id, params, t, x, y):
+        xdim, ydim = len(x), len(y)
+        with torch.cuda.device(self.device):
+            u, v = self.empty(ydim, xdim), self.empty(ydim, xdim)
+            ws, wsz = self.workspace(xdim, ydim)
+            p = nat.darray(params)
+            nat.check(nat.lib.dlb_flow_eval_grid(
+                flow_id, p, len(params), float(t), nat.dptr(x), xdim, nat.dptr(y), ydim,
+                u.data_ptr(), v.data_ptr(), ws, wsz, self.stream()))
+        return u, v
+
+    def flow_eval_points(self, flow_id, dim, params, t, pts):
+        """pts: [dim, n] device tensor -> [dim, n] velocities."""
+        n = pts.shape[1]
+        with torch.cuda.device(self.device):
+            out = self.empty(dim, n)
+            p = nat.darray(params)
+            nat.check(nat.lib.dlb_flow_eval_points(
+                flow_id, p, len(params), float(t), pts[0].data_ptr(), pts[1].data_ptr(),
+                pts[2].data_ptr() if dim == 3 else None, n, out[0].data_ptr(), out[1].data_ptr(),
+                out[2].data_ptr() if dim == 3 else None, self.stream()))
+        return out
+
+    # -- ridge field ------------------------------------------------------------------
+    def ridge_field(self, field, xi, x, y, edge_order, threshold=None):
+        xdim, ydim = len(x), len(y)
+        with torch.cuda.device(self.device):
+            dd, conc = self.empty(ydim, xdim), self.empty(ydim, xdim)
+            mask = self.empty(ydim, xdim, dtype=torch.uint8)
+            scratch = self.empty(ydim, xdim, 2)
+            ws, wsz = self.workspace(xdim, ydim)
+            nat.check(nat.lib.dlb_ridge_field(
+                field.data_ptr(), xi.data_ptr(), nat.dptr(x), xdim, nat.dptr(y), ydim,
+                int(edge_order), int(threshold is not None),
+                float(threshold if threshold is not None else 0.0), dd.data_ptr(),
+                conc.data_ptr(), mask.data_ptr(), scratch.data_ptr(), ws, wsz, self.stream()))
+        return dd, conc, mask
+
+    # -- FP64 peak --------------------------------------------------------------------
+    def dfma_peak(self, iters: int = 4096):
+        fl, ms = C.c_double(0.0), C.c_double(0.0)
+        with torch.cuda.device(self.device):
+            nat.check(nat.lib.dlb_dfma_peak(iters, C.byref(fl), C.byref(ms)))
+        return fl.value, ms.value

@@ -1,0 +1,33 @@
+// dynlab_b200 — shared declarations for the sm_100a kernels and the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dynlab_b200.h"
+
+#define DLB_MAX_CONSTS 16
+
+// Flow parameters after host-side preparation (flows.cuh: flow_prepare).  Passed to
+// kernels by value, so every thread reads them from the constant bank.
+struct FlowConsts {
+  double c[DLB_MAX_CONSTS];
+};
+
+void dlb_set_error(const char* fmt, ...);
+
+#define DLB_CUDA_CHECK(expr)                                                        \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      dlb_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,            \
+                    cudaGetErrorString(_e));                                        \
+      return DLB_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+// Workspace layout helpers (doubles).  The caller owns the workspace (a device buffer of
+// dlb_workspace_bytes(xdim, ydim) bytes); kernels use it for coordinate/coefficient arrays
+// and the work-stealing counter.
+static inline size_t dlb_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -1,0 +1,198 @@
+// Device twins of dynlab.flows (R:src/dynlab/flows.py:13-331).
+//
+// Each flow is split into
+//   flow_prepare(id, params, consts)  — host: parameter-only sub-expressions, evaluated in the
+//                                       reference's own operation order (separately rounded);
+//   flow_rhs<ID>(consts, t, Y, out)   — device: f(t, Y), inlined into the calling kernel.
+// The operation order of the reference's Python expressions is kept so that results differ
+// from numpy only through libm-vs-CUDA transcendental rounding and FMA contraction.
+#pragma once
+#include "common.cuh"
+#include "dmath.cuh"
+
+#define DLB_PI 3.141592653589793  // np.pi
+
+struct FlowInfo {
+  const char* name;
+  int dim;
+  int nparams;
+};
+
+static const FlowInfo k_flow_info[DLB_FLOW_COUNT] = {
+    {"double_gyre", 2, 3},
+    {"autonomous_double_gyre", 2, 0},
+    {"bickley_jet", 2, 10},
+    {"glider", 2, 0},
+    {"hills_vortex", 2, 0},
+    {"sigmoidal", 2, 0},
+    {"autonomous_duffing_oscillator", 2, 0},
+    {"duffing_oscillator", 2, 3},
+    {"pendulum", 2, 3},
+    {"hurricane", 2, 3},
+    {"van_der_pol_oscillator", 2, 4},
+    {"bead_on_a_rotating_hoop", 2, 2},
+    {"lotka_volterra", 2, 4},
+    {"abc", 3, 4},
+    {"lorenz", 3, 3},
+};
+
+// Host-side parameter preparation.  Returns false on a bad id / parameter count.
+static inline bool flow_prepare(int id, const double* p, int n_params, FlowConsts* fc) {
+  if (id < 0 || id >= DLB_FLOW_COUNT) return false;
+  if (n_params != k_flow_info[id].nparams) return false;
+  if (n_params > 0 && p == nullptr) return false;
+  memset(fc, 0, sizeof(*fc));
+  double* c = fc->c;
+  switch (id) {
+    case DLB_FLOW_DOUBLE_GYRE: {  // A, w, e  (flows.py:27-33)
+      const double A = p[0], w = p[1], e = p[2];
+      c[0] = w;
+      c[1] = e;
+      c[2] = 2 * e;            // `2*e*np.sin(w*t)` associates as (2*e)*sin
+      c[3] = -DLB_PI * A;      // `-np.pi*A*...`
+      c[4] = DLB_PI * A;       // `np.pi*A*...`
+    } break;
+    case DLB_FLOW_BICKLEY_JET: {  // flows.py:84-96
+      const double scale = p[9];
+      const double U0 = p[0] / scale, L = p[1] / scale, re = p[2] / scale;
+      const double A2 = p[3], A3 = p[4];
+      const double c2 = p[5] * U0, c3 = p[6] * U0, k2 = p[7] / re, k3 = p[8] / re;
+      c[0] = U0;
+      c[1] = L;
+      c[2] = c2;
+      c[3] = c3;
+      c[4] = k2;
+      c[5] = k3;
+      c[6] = 2 * A3 * U0;        // u: 2*A3*U0*tanh*sech2*cos(...)
+      c[7] = 2 * A2 * U0;
+      c[8] = -k3 * A3 * L * U0;  // v: -k3*A3*L*U0*sech2*sin(...)
+      c[9] = k2 * A2 * L * U0;
+    } break;
+    case DLB_FLOW_HURRICANE: {  // eye_alpha, eye_omega, eye_amplitude (flows.py:216-221)
+      const double sq = sqrt(1.0 + 4.0 * p[0]);
+      c[0] = p[0];
+      c[1] = p[1];
+      c[2] = p[2];
+      c[3] = 1.0 / sq;           // beta
+      c[4] = 0.5 * (1.0 + sq);   // y offset
+    } break;
+    case DLB_FLOW_BEAD:  // epsilon, gamma (flows.py:260-262)
+      c[0] = 1 / p[0];
+      c[1] = p[1];
+      break;
+    default:
+      for (int i = 0; i < n_params; ++i) c[i] = p[i];
+  }
+  return true;
+}
+
+// f(t, Y) for flow ID.  Y/out have k_flow_info[ID].dim entries.
+template <int ID>
+__device__ __forceinline__ void flow_rhs(const FlowConsts& fc, double t, const double* Y,
+                                         double* out) {
+  const double* c = fc.c;
+  const double x = Y[0], y = Y[1];
+  if constexpr (ID == DLB_FLOW_DOUBLE_GYRE) {
+    const double s = dm::sin(c[0] * t);
+    const double a = c[1] * s;
+    const double b = 1 - c[2] * s;
+    const double f = a * (x * x) + b * x;
+    const double dfdx = 2 * a * x + b;
+    double sf, cf, sy, cy;
+    dm::sincos(DLB_PI * f, &sf, &cf);
+    dm::sincos(y * DLB_PI, &sy, &cy);
+    out[0] = c[3] * sf * cy;
+    out[1] = c[4] * cf * sy * dfdx;
+  } else if constexpr (ID == DLB_FLOW_AUTONOMOUS_DOUBLE_GYRE) {
+    double sx, cx, sy, cy;
+    dm::sincos(DLB_PI * x, &sx, &cx);
+    dm::sincos(y * DLB_PI, &sy, &cy);
+    out[0] = -DLB_PI * sx * cy;
+    out[1] = DLB_PI * cx * sy;
+  } else if constexpr (ID == DLB_FLOW_BICKLEY_JET) {
+    const double yl = y / c[1];
+    const double ch = 1 / cosh(yl);
+    const double sech2 = ch * ch, th = tanh(yl);
+    double s3, c3, s2, c2;
+    dm::sincos(c[5] * (x - c[3] * t), &s3, &c3);
+    dm::sincos(c[4] * (x - c[2] * t), &s2, &c2);
+    out[0] = c[0] * sech2 + c[6] * th * sech2 * c3 + c[7] * th * sech2 * c2;
+    out[1] = c[8] * sech2 * s3 - c[9] * sech2 * s2;
+  } else if constexpr (ID == DLB_FLOW_GLIDER) {
+    const double r = sqrt(x * x + y * y);
+    const double th2 = -2 * atan2(y, x);
+    double s, cs;
+    dm::sincos(th2, &s, &cs);
+    s = 1.2 * s;
+    cs = 1.4 - cs;
+    out[0] = r * (-y * s - cs * x);
+    out[1] = r * (x * s - cs * y) - 1;
+  } else if constexpr (ID == DLB_FLOW_HILLS_VORTEX) {
+    out[0] = 2.0 * x * y;
+    out[1] = -2.0 * (2.0 * x * x - 1.0) - 2.0 * y * y;
+  } else if constexpr (ID == DLB_FLOW_SIGMOIDAL) {
+    out[0] = 0.4 * tanh(10.0 * (x - 0.5 * t));
+    out[1] = y * 0;
+  } else if constexpr (ID == DLB_FLOW_AUTONOMOUS_DUFFING) {
+    out[0] = y;
+    out[1] = x - x * x * x;
+  } else if constexpr (ID == DLB_FLOW_DUFFING) {  // A, gamma, omega
+    out[0] = y;
+    out[1] = x - x * x * x - c[1] * y + c[0] * dm::sin(c[2] * t);
+  } else if constexpr (ID == DLB_FLOW_PENDULUM) {  // A, gamma, omega
+    out[0] = y;
+    out[1] = -dm::sin(x) - c[1] * y + c[0] * dm::sin(c[2] * t);
+  } else if constexpr (ID == DLB_FLOW_HURRICANE) {
+    const double yt = y - c[4];
+    const double den = x * x + yt * yt + c[0];
+    out[0] = -yt / den - c[3];
+    out[1] = x / den + c[2] * y * dm::cos(c[1] * t);
+  } else if constexpr (ID == DLB_FLOW_VAN_DER_POL) {  // A, mu, gamma, omega
+    out[0] = y;
+    out[1] = c[1] * (1 - x * x) * y - x - c[2] * y + c[0] * dm::sin(c[3] * t);
+  } else if constexpr (ID == DLB_FLOW_BEAD) {  // 1/epsilon, gamma
+    double s, cs;
+    dm::sincos(x, &s, &cs);
+    out[0] = y;
+    out[1] = c[0] * (s * (c[1] * cs - 1) - y);
+  } else if constexpr (ID == DLB_FLOW_LOTKA_VOLTERRA) {  // alpha, beta, gamma, delta
+    out[0] = c[0] * x - c[1] * x * y;
+    out[1] = c[3] * x * y - c[2] * y;
+  } else if constexpr (ID == DLB_FLOW_ABC) {  // ABC_Amplitude, A, B, C
+    const double z = Y[2];
+    const double At = c[1] + c[0] * dm::sin(DLB_PI * t);
+    double sx, cx, sy, cy, sz, cz;
+    dm::sincos(x, &sx, &cx);
+    dm::sincos(y, &sy, &cy);
+    dm::sincos(z, &sz, &cz);
+    out[0] = At * sz + c[3] * cy;
+    out[1] = c[2] * sx + At * cz;
+    out[2] = c[3] * sy + c[2] * cx;
+  } else if constexpr (ID == DLB_FLOW_LORENZ) {  // sigma, rho, beta
+    const double z = Y[2];
+    out[0] = c[0] * (y - x);
+    out[1] = x * (c[1] - z) - y;
+    out[2] = x * y - c[2] * z;
+  }
+}
+
+// Run the statement block with `constexpr int ID` bound to the runtime flow id.
+#define DLB_DISPATCH_FLOW(id, ...)                                           \
+  switch (id) {                                                              \
+    case 0: { constexpr int ID = 0; __VA_ARGS__; } break;                           \
+    case 1: { constexpr int ID = 1; __VA_ARGS__; } break;                           \
+    case 2: { constexpr int ID = 2; __VA_ARGS__; } break;                           \
+    case 3: { constexpr int ID = 3; __VA_ARGS__; } break;                           \
+    case 4: { constexpr int ID = 4; __VA_ARGS__; } break;                           \
+    case 5: { constexpr int ID = 5; __VA_ARGS__; } break;                           \
+    case 6: { constexpr int ID = 6; __VA_ARGS__; } break;                           \
+    case 7: { constexpr int ID = 7; __VA_ARGS__; } break;                           \
+    case 8: { constexpr int ID = 8; __VA_ARGS__; } break;                           \
+    case 9: { constexpr int ID = 9; __VA_ARGS__; } break;                           \
+    case 10: { constexpr int ID = 10; __VA_ARGS__; } break;                         \
+    case 11: { constexpr int ID = 11; __VA_ARGS__; } break;                         \
+    case 12: { constexpr int ID = 12; __VA_ARGS__; } break;                         \
+    case 13: { constexpr int ID = 13; __VA_ARGS__; } break;                         \
+    case 14: { constexpr int ID = 14; __VA_ARGS__; } break;                         \
+    default: break;                                                          \
+  }

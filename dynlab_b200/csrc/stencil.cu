@@ -1,0 +1,653 @@
+// K2 / K3 / ridge field — np.gradient-exact stencils fused with the 2x2 eigen epilogues.
+//
+// K2 (FTLE): replaces R:src/dynlab/diagnostics/lagrangian.py:50-78 (and :130-167 with Xi_max)
+// K3 (Eulerian): replaces R:src/dynlab/diagnostics/_base_classes.py:110-111 and the per-point
+//     loops of R:src/dynlab/diagnostics/eulerian.py:47-59, :159-195, :317-343
+// ridge: replaces R:src/dynlab/diagnostics/_base_classes.py:216-268 (up to the contour call)
+// np.gradient semantics: numpy/lib/_function_base_impl.py:1246-1384 — per axis, uniform iff all
+// coordinate differences equal the first one exactly (:1246-1251); uniform interior
+// (f[i+1]-f[i-1])/(2h) (:1305), non-uniform interior a f[i-1] + b f[i] + c f[i+1] (:1307-1318),
+// edge_order 1 two-point (:1321-1334), edge_order 2 three-point (:1337-1372).
+//
+// B200 mapping (HBM-bound, 24 B per point): one warp owns a strip of 32 consecutive columns and
+// walks down a chunk of rows keeping the rows i-1, i, i+1 of its column in registers, so every
+// element is fetched from DRAM once (row loads are 256/512 B coalesced per warp); the x
+// neighbours come from L1 (the line was fetched one iteration earlier by the same warp).
+// Coefficients are precomputed per row / per column on the host with numpy's own formulas
+// (true divisions), so the kernel has no FP64 divides on the interior path.  The grid is a
+// multiple of the SM count and warps grid-stride over (strip, row-chunk) tasks.
+#include <math_constants.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int ST_BLOCK = 256;
+constexpr int ST_ROWS = 32;  // rows per warp task
+
+// Per-axis gradient description (device pointers into the workspace).
+struct Axis {
+  const double* ca;  // [n] 3-point coefficient on f[i-1] (or shifted at the edges)
+  const double* cb;  // [n]
+  const double* cc;  // [n]
+  long long n;
+  double inv2h;    // uniform: 1/(2h)
+  double w_first;  // edge_order 1: 1/dx_0
+  double w_last;   // edge_order 1: 1/dx_{n-1}
+  int uniform;
+};
+
+struct StencilParams {
+  Axis ax, ay;
+  long long nloc, grow0;        // local slab: rows [grow0, grow0+nloc)
+  long long out_row0, out_rows; // global rows to produce
+  int edge_order;
+  // inputs
+  const double2* fm;  // FTLE: [nloc][xdim] (Phi_x, Phi_y)
+  const double* u;    // Euler: [nloc][xdim]
+  const double* v;
+  const double* xi_in;  // ridge: [ydim][xdim][2]
+  // outputs
+  double* field;
+  double2* xi;
+  uint8_t* mask;
+  double* conc;
+  double scale;      // FTLE: 1/(2|T|)
+  double threshold;  // ridge
+  int use_threshold;
+  int xi_mode;
+  int negate;
+};
+
+enum { KIND_FTLE = 0, KIND_EULER = 1 };
+
+// ---- symmetric 2x2 eigen helpers ----
+
+// Largest / smallest eigenvalue of [[a, b], [b, d]], closed form.
+__device__ __forceinline__ double eig_sym_closed(double a, double b, double d, bool want_max) {
+  const double hm = 0.5 * (a - d);
+  const double r = sqrt(fma(hm, hm, b * b));
+  const double m = 0.5 * (a + d);
+  return want_max ? m + r : m - r;
+}
+
+// Eigenpair with the ordering and eigenvector sign np.linalg.eig (LAPACK dgeev: dlahqr's
+// deflation test + dlanv2's standardisation) produces for a symmetric 2x2 matrix, followed by
+// the reference's argsort selection (R:lagrangian.py:150-152, R:eulerian.py:327-330).
+__device__ __forceinline__ void eig_sym_lapack(double a, double b, double d, bool want_max,
+                                               double* w, double* vx, double* vy) {
+  const double ulp = 2.220446049250313e-16;      // dlamch('P')
+  const double smlnum = 2.0041683600089728e-292;  // dlamch('S') * (n / ulp), n = 2
+  bool deflate = (b == 0.0) || (fabs(b) <= smlnum);
+  if (!deflate) {  // dlahqr's conservative small-subdiagonal test
+    const double tst = fabs(a) + fabs(d);
+    if (fabs(b) <= ulp * tst) {
+      const double ab = fabs(b), ba = fabs(b);
+      const double aa = fmax(fabs(d), fabs(a - d)), bb = fmin(fabs(d), fabs(a - d));
+      const double s = aa + ab;
+      if (ba * (ab / s) <= fmax(smlnum, ulp * (bb * (aa / s)))) deflate = true;
+    }
+  }
+  double w0, w1, cs, sn;
+  if (deflate) {
+    w0 = a;
+    w1 = d;
+    cs = 1.0;
+    sn = 0.0;
+  } else {  // dlanv2 with c == b: always the real-eigenvalue branch
+    const double p = 0.5 * (a - d);
+    const double bcmax = fabs(b), bcmis = fabs(b);
+    const double sc = fmax(fabs(p), bcmax);
+    double z = p / sc * p + bcmax / sc * bcmis;
+    z = p + copysign(sqrt(sc) * sqrt(z), p);
+    w0 = d + z;
+    w1 = d - bcmax / z * bcmis;
+    const double tau = hypot(b, z);
+    cs = z / tau;
+    sn = b / tau;
+  }
+  // eigenvectors: column 0 = (cs, sn) for w0, column 1 = (-sn, cs) for w1.
+  // argsort ascending: idx[-1] is 0 only if w0 > w1; idx[0] is 1 only if w0 > w1.
+  const bool first_is_larger = (w0 > w1);
+  const bool take0 = want_max ? first_is_larger : !first_is_larger;
+  *w = take0 ? w0 : w1;
+  *vx = take0 ? cs : -sn;
+  *vy = take0 ? sn : cs;
+}
+
+// R:src/dynlab/utils.py:41-45
+__device__ __forceinline__ void force_eigenvector(double* vx, double* vy) {
+  const double a0 = fabs(*vx), a1 = fabs(*vy);
+  if ((a0 >= a1 && *vx < 0) || (a0 < a1 && *vy < 0)) {
+    *vx = -*vx;
+    *vy = -*vy;
+  }
+}
+
+// ---- gradient of a 2-component field at one node ----
+// s0, s1, s2 are the three samples the formula uses along the axis (already shifted at the
+// edges); `kind`: 0 interior, 1 first edge, 2 last edge.
+__device__ __forceinline__ double grad3(const Axis& A, long long i, int edge_order, double m,
+                                        double c, double p) {
+  // interior: (m, c, p) = f[i-1], f[i], f[i+1]
+  if (A.uniform) return (p - m) * A.inv2h;
+  return fma(A.cc[i], p, fma(A.cb[i], c, A.ca[i] * m));
+}
+
+struct Grad2 {
+  double d0dx, d0dy, d1dx, d1dy;
+};
+
+// Loader: at(local_row, col) -> double2.
+template <class Loader>
+__device__ __forceinline__ void edge_axis_x(const StencilParams& P, const Loader& ld,
+                                            long long lrow, long long j, double2 C, double2 L,
+                                            double2 R, double* g0, double* g1) {
+  const Axis& A = P.ax;
+  const long long n = A.n;
+  if (j > 0 && j < n - 1) {
+    *g0 = grad3(A, j, P.edge_order, L.x, C.x, R.x);
+    *g1 = grad3(A, j, P.edge_order, L.y, C.y, R.y);
+  } else if (P.edge_order == 1) {
+    if (j == 0) {  // (f[1] - f[0]) / dx_0
+      *g0 = (R.x - C.x) * A.w_first;
+      *g1 = (R.y - C.y) * A.w_first;
+    } else {  // (f[n-1] - f[n-2]) / dx_n
+      *g0 = (C.x - L.x) * A.w_last;
+      *g1 = (C.y - L.y) * A.w_last;
+    }
+  } else {
+    const double a = A.ca[j], b = A.cb[j], c = A.cc[j];
+    if (j == 0) {  // a f[0] + b f[1] + c f[2]
+      const double2 X = ld.at(lrow, 2);
+      *g0 = fma(c, X.x, fma(b, R.x, a * C.x));
+      *g1 = fma(c, X.y, fma(b, R.y, a * C.y));
+    } else {  // a f[n-3] + b f[n-2] + c f[n-1]
+      const double2 X = ld.at(lrow, n - 3);
+      *g0 = fma(c, C.x, fma(b, L.x, a * X.x));
+      *g1 = fma(c, C.y, fma(b, L.y, a * X.y));
+    }
+  }
+}
+
+template <class Loader>
+__device__ __forceinline__ void edge_axis_y(const StencilParams& P, const Loader& ld,
+                                            long long gi, long long j, double2 C, double2 U,
+                                            double2 D, double* g0, double* g1) {
+  const Axis& A = P.ay;
+  const long long n = A.n;
+  if (gi > 0 && gi < n - 1) {
+    *g0 = grad3(A, gi, P.edge_order, U.x, C.x, D.x);
+    *g1 = grad3(A, gi, P.edge_order, U.y, C.y, D.y);
+  } else if (P.edge_order == 1) {
+    if (gi == 0) {
+      *g0 = (D.x - C.x) * A.w_first;
+      *g1 = (D.y - C.y) * A.w_first;
+    } else {
+      *g0 = (C.x - U.x) * A.w_last;
+      *g1 = (C.y - U.y) * A.w_last;
+    }
+  } else {
+    const double a = A.ca[gi], b = A.cb[gi], c = A.cc[gi];
+    if (gi == 0) {
+      const double2 X = ld.at(2 - P.grow0, j);
+      *g0 = fma(c, X.x, fma(b, D.x, a * C.x));
+      *g1 = fma(c, X.y, fma(b, D.y, a * C.y));
+    } else {
+      const double2 X = ld.at(n - 3 - P.grow0, j);
+      *g0 = fma(c, C.x, fma(b, U.x, a * X.x));
+      *g1 = fma(c, C.y, fma(b, U.y, a * X.y));
+    }
+  }
+}
+
+struct LoaderAoS {
+  const double2* p;
+  long long xdim;
+  __device__ __forceinline__ double2 at(long long lrow, long long j) const {
+    return __ldg(p + lrow * xdim + j);
+  }
+};
+
+struct LoaderSoA {
+  const double* u;
+  const double* v;
+  long long xdim;
+  __device__ __forceinline__ double2 at(long long lrow, long long j) const {
+    const long long k = lrow * xdim + j;
+    return make_double2(__ldg(u + k), __ldg(v + k));
+  }
+};
+
+// MODE: for KIND_FTLE unused; for KIND_EULER one of dlb_euler_mode.
+template <int KIND, int MODE, bool XI, class Loader>
+__global__ void __launch_bounds__(ST_BLOCK) stencil_kernel(const StencilParams P, const Loader ld) {
+  const long long xdim = P.ax.n, ydim = P.ay.n;
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * ST_BLOCK + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * ST_BLOCK) >> 5;
+  const long long nstrips = (xdim + 31) / 32;
+  const long long nchunks = (P.out_rows + ST_ROWS - 1) / ST_ROWS;
+  const long long ntasks = nstrips * nchunks;
+
+  for (long long task = warp; task < ntasks; task += nwarps) {
+    const long long chunk = task / nstrips;
+    const long long strip = task - chunk * nstrips;
+    const long long jj = strip * 32 + lane;
+    const bool valid = jj < xdim;
+    const long long j = valid ? jj : xdim - 1;
+    const long long jl = (j > 0) ? j - 1 : 0;
+    const long long jr = (j < xdim - 1) ? j + 1 : xdim - 1;
+    const long long g0 = P.out_row0 + chunk * ST_ROWS;
+    const long long g1 = (g0 + ST_ROWS < P.out_row0 + P.out_rows) ? g0 + ST_ROWS
+                                                                   : P.out_row0 + P.out_rows;
+    // rolling window over rows (local row = global row - grow0)
+    double2 U = ld.at(((g0 > 0) ? g0 - 1 : 0) - P.grow0, j);
+    double2 C = ld.at(g0 - P.grow0, j);
+    double2 D = ld.at(((g0 + 1 < ydim) ? g0 + 1 : ydim - 1) - P.grow0, j);
+    for (long long gi = g0; gi < g1; ++gi) {
+      const long long lrow = gi - P.grow0;
+      // prefetch the row after next while this one is computed
+      const long long gnn = (gi + 2 < ydim) ? gi + 2 : ydim - 1;
+      double2 Dn = make_double2(0.0, 0.0);
+      if (gi + 1 < g1) Dn = ld.at(gnn - P.grow0, j);
+      const double2 L = ld.at(lrow, jl);
+      const double2 R = ld.at(lrow, jr);
+
+      double d0dx, d1dx, d0dy, d1dy;
+      edge_axis_x(P, ld, lrow, j, C, L, R, &d0dx, &d1dx);
+      edge_axis_y(P, ld, gi, j, C, U, D, &d0dy, &d1dy);
+
+      const long long o = (gi - P.out_row0) * xdim + j;
+      if (KIND == KIND_FTLE) {
+        // JF = [[dfxdx, dfxdy], [dfydx, dfydy]], C = JF^T JF   (lagrangian.py:65-66)
+        const double c11 = fma(d0dx, d0dx, d1dx * d1dx);
+        const double c12 = fma(d0dx, d0dy, d1dx * d1dy);
+        const double c22 = fma(d0dy, d0dy, d1dy * d1dy);
+        double lam, vx = 0.0, vy = 0.0;
+        if (XI) {
+          eig_sym_lapack(c11, c12, c22, true, &lam, &vx, &vy);
+          if (P.xi_mode == DLB_XI_FORCED) force_eigenvector(&vx, &vy);
+        } else {
+          lam = eig_sym_closed(c11, c12, c22, true);
+        }
+        // lagrangian.py:70-73
+        const double out = (lam >= 1.0) ? P.scale * log(lam) : 0.0;
+        if (valid) {
+          P.field[o] = out;
+          if (XI) P.xi[o] = make_double2(vx, vy);
+        }
+      } else {
+        // S = 0.5 (G + G^T), G = [[dudx, dudy], [dvdx, dvdy]]   (eulerian.py:52-53)
+        const double a = d0dx, d = d1dy, b = 0.5 * (d0dy + d1dx);
+        double out, vx = 0.0, vy = 0.0;
+        bool masked = false;
+        if (MODE == DLB_EULER_S_MIN || MODE == DLB_EULER_S_MAX) {
+          const bool want_max = (MODE == DLB_EULER_S_MAX);
+          if (XI) {
+            eig_sym_lapack(a, b, d, want_max, &out, &vx, &vy);
+            if (P.xi_mode == DLB_XI_FORCED) force_eigenvector(&vx, &vy);
+          } else {
+            out = eig_sym_closed(a, b, d, want_max);
+          }
+          if (P.negate) out = -out;
+        } else {
+          const double uu = C.x, vv = C.y;
+          const double v2 = fma(uu, uu, vv * vv);  // eulerian.py:187
+          double num;
+          if (MODE == DLB_EULER_RATE)  // V . (J^T S J) V, eulerian.py:160-165
+            num = fma(a * vv, vv, fma(-2.0 * b * uu, vv, d * uu * uu));
+          else  // V . (tr(S) I - 2 S) V, eulerian.py:167-171
+            num = fma((a - d) * vv, vv, fma(-4.0 * b * uu, vv, (d - a) * uu * uu));
+          masked = (v2 == 0.0);  // eulerian.py:188-192
+          out = masked ? 0.0 : num / v2;
+        }
+        if (valid) {
+          P.field[o] = out;
+          if (XI) P.xi[o] = make_double2(vx, vy);
+          if (P.mask) P.mask[o] = masked ? 1 : 0;
+        }
+      }
+      U = C;
+      C = D;
+      D = Dn;
+    }
+  }
+}
+
+// ---- ridge field: two passes over a scalar field ----
+struct LoaderScalar {
+  const double* f;
+  long long xdim;
+  __device__ __forceinline__ double2 at(long long lrow, long long j) const {
+    return make_double2(__ldg(f + lrow * xdim + j), 0.0);
+  }
+};
+
+// pass 1: (dfdx, dfdy) of the field -> scratch as AoS double2
+__global__ void __launch_bounds__(ST_BLOCK) ridge_pass1(const StencilParams P, const LoaderScalar ld,
+                                                        double2* grad) {
+  const long long xdim = P.ax.n, ydim = P.ay.n;
+  const long long total = xdim * ydim;
+  for (long long k = (long long)blockIdx.x * ST_BLOCK + threadIdx.x; k < total;
+       k += (long long)gridDim.x * ST_BLOCK) {
+    const long long i = k / xdim, j = k - i * xdim;
+    const double2 C = ld.at(i, j);
+    const double2 L = ld.at(i, j > 0 ? j - 1 : 0), R = ld.at(i, j < xdim - 1 ? j + 1 : xdim - 1);
+    const double2 U = ld.at(i > 0 ? i - 1 : 0, j), D = ld.at(i < ydim - 1 ? i + 1 : ydim - 1, j);
+    double gx, gy, t0, t1;
+    edge_axis_x(P, ld, i, j, C, L, R, &gx, &t0);
+    edge_axis_y(P, ld, i, j, C, U, D, &gy, &t1);
+    grad[k] = make_double2(gx, gy);
+  }
+}
+
+// pass 2: Hessian from the first derivatives, directional derivative, concavity, masks
+// (_base_classes.py:218-268).
+__global__ void __launch_bounds__(ST_BLOCK) ridge_pass2(const StencilParams P, const LoaderAoS ld,
+                                                        const double* field) {
+  const long long xdim = P.ax.n, ydim = P.ay.n;
+  const long long total = xdim * ydim;
+  for (long long k = (long long)blockIdx.x * ST_BLOCK + threadIdx.x; k < total;
+       k += (long long)gridDim.x * ST_BLOCK) {
+    const long long i = k / xdim, j = k - i * xdim;
+    const double2 C = ld.at(i, j);  // (dfdx, dfdy)
+    const double2 L = ld.at(i, j > 0 ? j - 1 : 0), R = ld.at(i, j < xdim - 1 ? j + 1 : xdim - 1);
+    const double2 U = ld.at(i > 0 ? i - 1 : 0, j), D = ld.at(i < ydim - 1 ? i + 1 : ydim - 1, j);
+    double dfdxdx, dfdydx, dfdxdy, dfdydy;
+    edge_axis_x(P, ld, i, j, C, L, R, &dfdxdx, &dfdydx);  // d/dx of (dfdx, dfdy)
+    edge_axis_y(P, ld, i, j, C, U, D, &dfdxdy, &dfdydy);  // d/dy of (dfdx, dfdy)
+    const double x0 = P.xi_in[2 * k], x1 = P.xi_in[2 * k + 1];
+    // np.dot([dfdx, dfdy], Xi)   (:225-227)
+    const double dd = fma(C.y, x1, C.x * x0);
+    // np.dot(np.dot([[dfdxdx, dfdxdy], [dfdydx, dfdydy]], Xi), Xi)   (:228-235)
+    const double h0 = fma(dfdxdy, x1, dfdxdx * x0);
+    const double h1 = fma(dfdydy, x1, dfdydx * x0);
+    const double conc = fma(h1, x1, h0 * x0);
+    const double fv = field[k];
+    bool m = (fv <= 0.0) || (conc >= 0.0);           // :251-258
+    if (P.use_threshold) m = m || (fv <= P.threshold);  // :266-268
+    P.field[k] = dd;
+    P.conc[k] = conc;
+    P.mask[k] = m ? 1 : 0;
+  }
+}
+
+// ---- host: numpy's coefficient formulas ----
+struct HostAxis {
+  std::vector<double> ca, cb, cc;
+  double inv2h = 0, w_first = 0, w_last = 0;
+  int uniform = 1;
+};
+
+// numpy/lib/_function_base_impl.py:1246-1251, 1305-1372
+void build_axis(const double* c, long long n, int edge_order, HostAxis* H) {
+  H->ca.assign(n, 0.0);
+  H->cb.assign(n, 0.0);
+  H->cc.assign(n, 0.0);
+  std::vector<double> dx(n > 1 ? n - 1 : 0);
+  for (long long i = 0; i + 1 < n; ++i) dx[i] = c[i + 1] - c[i];
+  H->uniform = 1;
+  for (long long i = 1; i + 1 < n; ++i)
+    if (dx[i] != dx[0]) H->uniform = 0;
+  const double h = dx[0];
+  if (H->uniform) {
+    H->inv2h = 1.0 / (2. * h);
+    H->w_first = H->w_last = 1.0 / h;
+  } else {
+    for (long long i = 1; i + 1 < n; ++i) {
+      const double dx1 = dx[i - 1], dx2 = dx[i];
+      H->ca[i] = -(dx2) / (dx1 * (dx1 + dx2));
+      H->cb[i] = (dx2 - dx1) / (dx1 * dx2);
+      H->cc[i] = dx1 / (dx2 * (dx1 + dx2));
+    }
+    H->w_first = 1.0 / dx[0];
+    H->w_last = 1.0 / dx[n - 2];
+  }
+  if (edge_order == 2) {
+    if (H->uniform) {
+      H->ca[0] = -1.5 / h; H->cb[0] = 2. / h; H->cc[0] = -0.5 / h;
+      H->ca[n - 1] = 0.5 / h; H->cb[n - 1] = -2. / h; H->cc[n - 1] = 1.5 / h;
+    } else {
+      double dx1 = dx[0], dx2 = dx[1];
+      H->ca[0] = -(2. * dx1 + dx2) / (dx1 * (dx1 + dx2));
+      H->cb[0] = (dx1 + dx2) / (dx1 * dx2);
+      H->cc[0] = -dx1 / (dx2 * (dx1 + dx2));
+      dx1 = dx[n - 3];
+      dx2 = dx[n - 2];
+      H->ca[n - 1] = (dx2) / (dx1 * (dx1 + dx2));
+      H->cb[n - 1] = -(dx2 + dx1) / (dx1 * dx2);
+      H->cc[n - 1] = (2. * dx2 + dx1) / (dx2 * (dx1 + dx2));
+    }
+  }
+}
+
+int g_sms = 0;
+int num_sms() {
+  if (g_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      g_sms = 148;
+  }
+  return g_sms;
+}
+
+// Validate geometry, build + upload both axes into the workspace, fill P.ax / P.ay.
+int setup_axes(StencilParams& P, const double* h_x, int64_t xdim, const double* h_y, int64_t ydim,
+               int edge_order, void* d_workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (!h_x || !h_y || !d_workspace) {
+    dlb_set_error("stencil: null pointer");
+    return DLB_ERR_ARG;
+  }
+  if (edge_order > 2) {  // numpy :1255-1256
+    dlb_set_error("'edge_order' greater than 2 not supported");
+    return DLB_ERR_ARG;
+  }
+  if (edge_order < 1) {
+    dlb_set_error("'edge_order' must be 1 or 2");
+    return DLB_ERR_ARG;
+  }
+  if (xdim < edge_order + 1 || ydim < edge_order + 1) {  // numpy :1288-1291
+    dlb_set_error(
+        "Shape of array too small to calculate a numerical gradient, at least (edge_order + 1) "
+        "elements are required.");
+    return DLB_ERR_TOO_SMALL;
+  }
+  if (workspace_bytes < dlb_workspace_bytes(xdim, ydim)) {
+    dlb_set_error("workspace too small");
+    return DLB_ERR_WORKSPACE;
+  }
+  HostAxis hx, hy;
+  build_axis(h_x, xdim, edge_order, &hx);
+  build_axis(h_y, ydim, edge_order, &hy);
+  // workspace: 256 B header, x[xdim], y[ydim] (rk45.cu), then coefficients
+  double* base = (double*)((char*)d_workspace + 256) + (xdim + ydim);
+  double* dxa = base;
+  double* dya = base + 3 * xdim;
+  std::vector<double> stage(3 * (xdim + ydim));
+  memcpy(&stage[0], hx.ca.data(), sizeof(double) * xdim);
+  memcpy(&stage[xdim], hx.cb.data(), sizeof(double) * xdim);
+  memcpy(&stage[2 * xdim], hx.cc.data(), sizeof(double) * xdim);
+  memcpy(&stage[3 * xdim], hy.ca.data(), sizeof(double) * ydim);
+  memcpy(&stage[3 * xdim + ydim], hy.cb.data(), sizeof(double) * ydim);
+  memcpy(&stage[3 * xdim + 2 * ydim], hy.cc.data(), sizeof(double) * ydim);
+  // pageable source: cudaMemcpyAsync stages it before returning, so `stage` may die here
+  DLB_CUDA_CHECK(cudaMemcpyAsync(base, stage.data(), sizeof(double) * stage.size(),
+                                 cudaMemcpyHostToDevice, stream));
+  P.ax = Axis{dxa, dxa + xdim, dxa + 2 * xdim, xdim, hx.inv2h, hx.w_first, hx.w_last, hx.uniform};
+  P.ay = Axis{dya, dya + ydim, dya + 2 * ydim, ydim, hy.inv2h, hy.w_first, hy.w_last, hy.uniform};
+  P.edge_order = edge_order;
+  return DLB_OK;
+}
+
+int check_slab(const StencilParams& P, int64_t ydim) {
+  if (P.out_rows < 0 || P.out_row0 < 0 || P.out_row0 + P.out_rows > ydim || P.grow0 < 0 ||
+      P.grow0 + P.nloc > ydim) {
+    dlb_set_error("stencil: slab outside the grid");
+    return DLB_ERR_ARG;
+  }
+  if (P.out_rows == 0) return DLB_OK;
+  // every row an output row's stencil touches must be local
+  long long lo = P.out_row0 > 0 ? P.out_row0 - 1 : 0;
+  long long hi = P.out_row0 + P.out_rows < ydim ? P.out_row0 + P.out_rows : ydim - 1;
+  if (P.edge_order == 2) {
+    if (P.out_row0 == 0 && hi < 2) hi = 2;
+    if (P.out_row0 + P.out_rows == ydim && lo > ydim - 3) lo = ydim - 3;
+  }
+  if (lo < P.grow0 || hi >= P.grow0 + P.nloc) {
+    dlb_set_error("stencil: halo rows missing (need global rows %lld..%lld, have %lld..%lld)", lo,
+                  hi, P.grow0, P.grow0 + P.nloc - 1);
+    return DLB_ERR_ARG;
+  }
+  return DLB_OK;
+}
+
+unsigned stencil_grid(const StencilParams& P) {
+  const long long nstrips = (P.ax.n + 31) / 32;
+  const long long nchunks = (P.out_rows + ST_ROWS - 1) / ST_ROWS;
+  const long long ntasks = nstrips * nchunks;
+  const long long warps_per_block = ST_BLOCK / 32;
+  long long blocks = (ntasks + warps_per_block - 1) / warps_per_block;
+  const long long cap = (long long)num_sms() * 8;  // 8 CTAs of 256 threads = 2048 threads/SM
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+}  // namespace
+
+extern "C" int dlb_ftle_stencil(const double* d_flow_map, int64_t nloc, int64_t grow0,
+                                const double* h_x, int64_t xdim, const double* h_y, int64_t ydim,
+                                int edge_order, double t_span, int64_t out_row0, int64_t out_rows,
+                                double* d_ftle, double* d_xi, int xi_mode, void* d_workspace,
+                                size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!d_flow_map || !d_ftle || (xi_mode != DLB_XI_NONE && !d_xi)) {
+    dlb_set_error("dlb_ftle_stencil: null pointer");
+    return DLB_ERR_ARG;
+  }
+  StencilParams P;
+  memset(&P, 0, sizeof(P));
+  int rc = setup_axes(P, h_x, xdim, h_y, ydim, edge_order, d_workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  P.nloc = nloc;
+  P.grow0 = grow0;
+  P.out_row0 = out_row0;
+  P.out_rows = out_rows;
+  rc = check_slab(P, ydim);
+  if (rc || out_rows == 0) return rc;
+  P.fm = (const double2*)d_flow_map;
+  P.field = d_ftle;
+  P.xi = (double2*)d_xi;
+  P.xi_mode = xi_mode;
+  P.scale = 1.0 / (2.0 * fabs(t_span));  // lagrangian.py:71
+  LoaderAoS ld{P.fm, xdim};
+  const unsigned grid = stencil_grid(P);
+  if (xi_mode == DLB_XI_NONE)
+    stencil_kernel<KIND_FTLE, 0, false, LoaderAoS><<<grid, ST_BLOCK, 0, stream>>>(P, ld);
+  else
+    stencil_kernel<KIND_FTLE, 0, true, LoaderAoS><<<grid, ST_BLOCK, 0, stream>>>(P, ld);
+  DLB_CUDA_CHECK(cudaGetLastError());
+  return DLB_OK;
+}
+
+extern "C" int dlb_euler_stencil(int mode, const double* d_u, const double* d_v, int64_t nloc,
+                                 int64_t grow0, const double* h_x, int64_t xdim, const double* h_y,
+                                 int64_t ydim, int edge_order, int64_t out_row0, int64_t out_rows,
+                                 int negate, double* d_field, uint8_t* d_mask, double* d_xi,
+                                 int xi_mode, void* d_workspace, size_t workspace_bytes,
+                                 void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!d_u || !d_v || !d_field || (xi_mode != DLB_XI_NONE && !d_xi)) {
+    dlb_set_error("dlb_euler_stencil: null pointer");
+    return DLB_ERR_ARG;
+  }
+  if (mode < DLB_EULER_S_MIN || mode > DLB_EULER_RATIO) {
+    dlb_set_error("dlb_euler_stencil: unknown mode %d", mode);
+    return DLB_ERR_ARG;
+  }
+  if ((mode == DLB_EULER_RATE || mode == DLB_EULER_RATIO) && (!d_mask || xi_mode != DLB_XI_NONE)) {
+    dlb_set_error("dlb_euler_stencil: rate/ratio need d_mask and produce no eigenvector");
+    return DLB_ERR_ARG;
+  }
+  StencilParams P;
+  memset(&P, 0, sizeof(P));
+  int rc = setup_axes(P, h_x, xdim, h_y, ydim, edge_order, d_workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  P.nloc = nloc;
+  P.grow0 = grow0;
+  P.out_row0 = out_row0;
+  P.out_rows = out_rows;
+  rc = check_slab(P, ydim);
+  if (rc || out_rows == 0) return rc;
+  P.u = d_u;
+  P.v = d_v;
+  P.field = d_field;
+  P.mask = d_mask;
+  P.xi = (double2*)d_xi;
+  P.xi_mode = xi_mode;
+  P.negate = negate;
+  LoaderSoA ld{d_u, d_v, xdim};
+  const unsigned grid = stencil_grid(P);
+  const bool xi = xi_mode != DLB_XI_NONE;
+#define LAUNCH(M)                                                                          \
+  if (xi)                                                                                  \
+    stencil_kernel<KIND_EULER, M, true, LoaderSoA><<<grid, ST_BLOCK, 0, stream>>>(P, ld);  \
+  else                                                                                     \
+    stencil_kernel<KIND_EULER, M, false, LoaderSoA><<<grid, ST_BLOCK, 0, stream>>>(P, ld);
+  switch (mode) {
+    case DLB_EULER_S_MIN: LAUNCH(DLB_EULER_S_MIN); break;
+    case DLB_EULER_S_MAX: LAUNCH(DLB_EULER_S_MAX); break;
+    case DLB_EULER_RATE:
+      stencil_kernel<KIND_EULER, DLB_EULER_RATE, false, LoaderSoA>
+          <<<grid, ST_BLOCK, 0, stream>>>(P, ld);
+      break;
+    default:
+      stencil_kernel<KIND_EULER, DLB_EULER_RATIO, false, LoaderSoA>
+          <<<grid, ST_BLOCK, 0, stream>>>(P, ld);
+  }
+#undef LAUNCH
+  DLB_CUDA_CHECK(cudaGetLastError());
+  return DLB_OK;
+}
+
+extern "C" int dlb_ridge_field(const double* d_field, const double* d_xi, const double* h_x,
+                               int64_t xdim, const double* h_y, int64_t ydim, int edge_order,
+                               int use_threshold, double threshold, double* d_dd, double* d_conc,
+                               uint8_t* d_mask, double* d_scratch, void* d_workspace,
+                               size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!d_field || !d_xi || !d_dd || !d_conc || !d_mask || !d_scratch) {
+    dlb_set_error("dlb_ridge_field: null pointer");
+    return DLB_ERR_ARG;
+  }
+  StencilParams P;
+  memset(&P, 0, sizeof(P));
+  int rc = setup_axes(P, h_x, xdim, h_y, ydim, edge_order, d_workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  P.nloc = ydim;
+  P.grow0 = 0;
+  P.out_row0 = 0;
+  P.out_rows = ydim;
+  P.xi_in = d_xi;
+  P.field = d_dd;
+  P.conc = d_conc;
+  P.mask = d_mask;
+  P.use_threshold = use_threshold;
+  P.threshold = threshold;
+  const long long total = (long long)xdim * ydim;
+  long long blocks = (total + ST_BLOCK - 1) / ST_BLOCK;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  LoaderScalar l1{d_field, xdim};
+  ridge_pass1<<<(unsigned)blocks, ST_BLOCK, 0, stream>>>(P, l1, (double2*)d_scratch);
+  DLB_CUDA_CHECK(cudaGetLastError());
+  LoaderAoS l2{(const double2*)d_scratch, xdim};
+  ridge_pass2<<<(unsigned)blocks, ST_BLOCK, 0, stream>>>(P, l2, d_field);
+  DLB_CUDA_CHECK(cudaGetLastError());
+  return DLB_OK;
+}

@@ -1,0 +1,266 @@
+"""Host-side bases of the diagnostics (mirror of R:src/dynlab/diagnostics/_base_classes.py).
+
+Same class names, constructor/compute signatures, attribute names and exception types as the
+reference; the work itself is enqueued on the GPU through ``dynlab_b200._engine.Engine``:
+
+  LagrangianDiagnostic2D.compute  -> K1 flow-map kernel over this rank's row slab
+                                     (reference: seed loop + integrator, :171-189)
+  EulerianDiagnostic2D.compute    -> device-resident (u, v) — uploaded, or evaluated by K0 —
+                                     handed to the K3 stencil (reference: np.gradient x2, :91-113)
+  RidgeExtractor2D.extract_ridges -> ridge-field kernel, then host contouring (:194-277)
+"""
+from __future__ import annotations
+
+import warnings
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+
+from .. import _native as nat
+from .. import sharding
+from .._engine import Engine, as_coord
+from .._resolve import resolve_flow
+from ..utils import (ODEINT_DEFAULT_TOL, RK45_DEFAULT_ATOL, RK45_DEFAULT_RTOL, odeint_wrapper,
+                     parse_integrator_kwargs, rk45_wrapper)
+
+
+class UnsupportedIntegratorError(NotImplementedError):
+    """``integrator=`` is not one of the device integrator sentinels."""
+
+
+class _LazyHost:
+    """Attribute that lives on the device until somebody reads it (then cached on the host)."""
+
+    def __init__(self, name):
+        self.dev, self.host = "_" + name + "_dev", "_" + name + "_host"
+
+    def __get__(self, obj, objtype=None):
+        if obj is None:
+            return self
+        host = obj.__dict__.get(self.host)
+        if host is None:
+            dev = obj.__dict__.get(self.dev)
+            if dev is None:
+                raise AttributeError(self.host[1:-5])
+            host = obj.__dict__[self.host] = Engine.get(dev.device).to_host(dev)
+        return host
+
+    def __set__(self, obj, value):
+        if isinstance(value, torch.Tensor) and value.is_cuda:
+            obj.__dict__[self.dev] = value
+            obj.__dict__.pop(self.host, None)
+        else:
+            obj.__dict__[self.host] = value
+            obj.__dict__.pop(self.dev, None)
+
+    def __delete__(self, obj):
+        obj.__dict__.pop(self.dev, None)
+        obj.__dict__.pop(self.host, None)
+
+
+class Diagnostic2D(ABC):
+    """Coordinate handling shared by every 2-D diagnostic (R:_base_classes.py:13-50)."""
+
+    @abstractmethod
+    def compute(self, x, y) -> None:
+        ys = (y if type(y) is np.ndarray else np.array(y)).squeeze()
+        xs = (x if type(x) is np.ndarray else np.array(x)).squeeze()
+        if ys.ndim > 1:
+            raise ValueError("y must be a 1-dimensional array.")
+        if xs.ndim > 1:
+            raise ValueError("x must be a 1-dimensional array.")
+        self.y, self.x = ys, xs
+        self.ydim, self.xdim = len(ys), len(xs)
+        # float64 copies for the kernels (np.gradient casts integer coordinates the same way)
+        self._yf, self._xf = as_coord(ys), as_coord(xs)
+
+    @staticmethod
+    def not_masked(*args) -> bool:
+        """True when none of the values is ``np.ma.masked`` (R:_base_classes.py:38-50)."""
+        return not any(a is np.ma.masked for a in args)
+
+
+class EulerianDiagnostic2D(Diagnostic2D, ABC):
+    """Velocity-field intake for the Eulerian diagnostics (R:_base_classes.py:53-113)."""
+
+    u = _LazyHost("u")
+    v = _LazyHost("v")
+
+    @abstractmethod
+    def compute(self, x, y, u, v, f=None, t=None, edge_order=1):
+        """Validates the inputs and leaves ``(u, v)`` on the device.  Returns the device
+        tensors; the gradients themselves are taken inside the fused K3 kernel."""
+        super().compute(x, y)
+        eng = Engine.get()
+        if u is not None and v is not None:
+            if isinstance(u, torch.Tensor) and isinstance(v, torch.Tensor):
+                ud, vd = u.squeeze(), v.squeeze()
+                if vd.ndim != 2:
+                    raise ValueError("v must be a 2-dimensional array.")
+                if ud.ndim != 2:
+                    raise ValueError("u must be a 2-dimensional array.")
+                ud = ud.to(eng.device, torch.float64).contiguous()
+                vd = vd.to(eng.device, torch.float64).contiguous()
+                self.u, self.v = ud, vd
+            else:
+                vh = (v if type(v) is np.ndarray else np.array(v)).squeeze()
+                uh = (u if type(u) is np.ndarray else np.array(u)).squeeze()
+                if vh.ndim != 2:
+                    raise ValueError("v must be a 2-dimensional array.")
+                if uh.ndim != 2:
+                    raise ValueError("u must be a 2-dimensional array.")
+                self.u, self.v = uh, vh
+                ud, vd = eng.to_device(uh), eng.to_device(vh)
+            for a in (ud, vd):
+                if tuple(a.shape) != (self.ydim, self.xdim):
+                    raise ValueError("when 1d, distances must match the length of the "
+                                     "corresponding dimension")
+        elif f is not None and t is not None:
+            _, fid, dim, params = resolve_flow(f)
+            if dim != 2:
+                raise ValueError("a 2-D diagnostic needs a 2-D flow")
+            ud, vd = eng.flow_eval_grid(fid, params, float(t), self._xf, self._yf)
+            self.u, self.v = ud, vd  # downloaded only if the user reads them
+        else:
+            raise RuntimeError(
+                "Either a velocity field (u, v) or a function and timestep from which to "
+                "calculate a velocity field must be passed to the compute function.")
+        if edge_order > 2:
+            raise ValueError("'edge_order' greater than 2 not supported")
+        return ud, vd
+
+    def _euler(self, mode, ud, vd, edge_order, negate=False, xi_mode=nat.XI_NONE):
+        """Run K3 on the whole grid (row-sharded when a process group is active)."""
+        eng = Engine.get()
+        rank, size = sharding.world()
+        if size == 1:
+            return eng.euler_stencil(mode, ud, vd, 0, self._xf, self._yf, edge_order, 0,
+                                     self.ydim, negate, xi_mode)
+        slab = sharding.partition(self.ydim, size, rank)
+        f = m = xi = None
+        if slab.rows:
+            f, m, xi = eng.euler_stencil(mode, ud[slab.lo:slab.hi], vd[slab.lo:slab.hi], slab.lo,
+                                         self._xf, self._yf, edge_order, slab.row0, slab.rows,
+                                         negate, xi_mode)
+
+        def gather(part, tail, dtype):
+            pad = torch.zeros((slab.rows_max, self.xdim) + tail, dtype=dtype, device=eng.device)
+            if part is not None:
+                pad[:slab.rows] = part
+            return sharding.gather_rows(pad, self.ydim, size)
+
+        need_mask = mode in (nat.EULER_RATE, nat.EULER_RATIO)
+        return (gather(f, (), torch.float64),
+                gather(m, (), torch.uint8) if need_mask else None,
+                gather(xi, (2,), torch.float64) if xi_mode != nat.XI_NONE else None)
+
+
+class LagrangianDiagnostic2D(Diagnostic2D, ABC):
+    """Flow-map builder (R:_base_classes.py:116-189)."""
+
+    flow_map = _LazyHost("flow_map")
+
+    def __init__(self, integrator=odeint_wrapper, num_threads: int = 1) -> None:
+        super().__init__()
+        self.num_threads = num_threads
+        self.integrator = integrator
+        # The reference builds a process pool for num_threads > 1 (:139-146); on the GPU every
+        # seed already has its own thread, so the value is validated and otherwise unused.
+        if not num_threads >= 1:
+            raise ValueError("num_threads must be an integer greater than 0.")
+        self.stats = {}
+
+    def _tolerances(self, kwargs):
+        if self.integrator is odeint_wrapper:
+            return parse_integrator_kwargs(kwargs, ODEINT_DEFAULT_TOL, ODEINT_DEFAULT_TOL)
+        if self.integrator is rk45_wrapper:
+            return parse_integrator_kwargs(kwargs, RK45_DEFAULT_RTOL, RK45_DEFAULT_ATOL)
+        raise UnsupportedIntegratorError(
+            f"integrator {self.integrator!r} cannot run on the device: use "
+            f"dynlab_b200.utils.odeint_wrapper (default) or rk45_wrapper; there is no CPU "
+            f"fallback for Python integrators")
+
+    @abstractmethod
+    def compute(self, x, y, f, t, **kwargs):
+        """Integrate this rank's row slab.  Returns ``(local, slab)`` where ``local`` is the
+        device tensor ``[slab.nloc, xdim, 2]`` with the own rows filled and the halo rows
+        exchanged; attribute ``flow_map`` (host ``[ydim, xdim, 2]``) is materialised lazily."""
+        super().compute(x, y)
+        if len(t) != 2:
+            raise ValueError("t must only have 2 values, t_0 and t_final")
+        kw = self._tolerances(kwargs)
+        _, fid, dim, params = resolve_flow(f)
+        if dim != 2:
+            raise ValueError("a 2-D diagnostic needs a 2-D flow")
+        atol = np.asarray(kw["atol"], dtype=np.float64)
+        if atol.ndim > 0:
+            if atol.shape != (2,):
+                raise ValueError("`atol` has wrong shape.")
+            if atol[0] != atol[1]:
+                raise NotImplementedError("per-component atol is only available through "
+                                          "dynlab_b200.utils.rk45_wrapper")
+            atol = atol[0]
+        if float(atol) < 0:
+            raise ValueError("`atol` must be positive.")
+        t0, tf = float(t[0]), float(t[1])
+        first = kw["first_step"]
+        if first is not None and first > abs(tf - t0):
+            raise ValueError("`first_step` exceeds bounds.")
+        if kw["rtol"] < 100 * np.finfo(float).eps:
+            warnings.warn("At least one element of `rtol` is too small. "
+                          f"Setting `rtol = np.maximum(rtol, {100 * np.finfo(float).eps})`.")
+
+        eng = Engine.get()
+        rank, size = sharding.world()
+        slab = sharding.partition(self.ydim, size, rank)
+        local = eng.empty(max(slab.nloc, 1), self.xdim, 2)
+        if slab.rows:
+            own = local[slab.halo_lo:slab.halo_lo + slab.rows]
+            eng.flow_map(fid, params, self._xf, self._yf, slab.row0, slab.rows, t0, tf,
+                         kw["rtol"], float(atol), kw["max_step"], first or 0.0, out=own)
+        self._counters_pending = slab.rows > 0
+        if size > 1:
+            sharding.exchange_halo(local, slab, self.ydim, rank, size)
+            pad = torch.zeros(slab.rows_max, self.xdim, 2, dtype=torch.float64, device=eng.device)
+            if slab.rows:
+                pad[:slab.rows] = local[slab.halo_lo:slab.halo_lo + slab.rows]
+            self.flow_map = sharding.gather_rows(pad, self.ydim, size)
+        else:
+            self.flow_map = local[:slab.nloc]
+        return local, slab
+
+    def _collect_stats(self):
+        """Read the integrator counters (after the results were synchronised) and warn about
+        seeds scipy would have ended with status -1; the reference keeps their last state
+        silently (R:_base_classes.py:180-182), so the values are kept."""
+        if getattr(self, "_counters_pending", False):
+            self.stats = Engine.get().read_counters()
+            self._counters_pending = False
+            if self.stats["failed"]:
+                warnings.warn(f"{self.stats['failed']} trajectories stopped early: required step "
+                              "size is less than spacing between numbers (scipy status -1)",
+                              RuntimeWarning)
+
+
+class RidgeExtractor2D(Diagnostic2D, ABC):
+    """Ridge extraction shared by LCS and iLES (R:_base_classes.py:192-277)."""
+
+    def extract_ridges(self, field, Xi, percentile, edge_order, debug=False):
+        """``field`` / ``Xi``: device tensors ``[ydim, xdim]`` / ``[ydim, xdim, 2]``.
+        The gradient/Hessian/mask stage runs on the device; the zero-contour of the masked
+        directional-derivative field is traced on the host (O(ridge length) output)."""
+        from .._contour import zero_contour_lines
+
+        eng = Engine.get()
+        threshold = None
+        if percentile:
+            # R:_base_classes.py:266-268 — np.percentile of the (unmasked) field values
+            threshold = float(np.percentile(eng.to_host(field), percentile))
+        dd, conc, mask = eng.ridge_field(field, Xi, self._xf, self._yf, edge_order, threshold)
+        dd_h = np.ma.MaskedArray(eng.to_host(dd), mask=eng.to_host(mask).astype(bool))
+        ridge_lines = zero_contour_lines(self.x, self.y, dd_h)
+        if debug:
+            self.directional_derivative = dd_h
+            self.concavity = np.ma.MaskedArray(eng.to_host(conc))
+        return ridge_lines

@@ -1,0 +1,81 @@
+"""FTLE and LCS (mirror of R:src/dynlab/diagnostics/lagrangian.py).
+
+Pipeline per ``compute``: K1 (flow map of this rank's row slab) -> halo rows -> K2 (np.gradient
+stencil + Cauchy-Green tensor + eigen + log, fused) -> gather -> one device-to-host copy of the
+field.  ``flow_map`` stays on the device until it is read.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _native as nat
+from .. import sharding
+from .._engine import Engine
+from ..utils import odeint_wrapper
+from ._base_classes import LagrangianDiagnostic2D, RidgeExtractor2D
+
+
+def _ftle_on_device(diag, local, slab, t, edge_order, xi_mode):
+    """K2 on this rank's slab, gathered to the full grid on every rank (device tensors)."""
+    eng = Engine.get()
+    rank, size = sharding.world()
+    if edge_order > 2:
+        raise ValueError("'edge_order' greater than 2 not supported")
+    t_span = abs(float(t[-1]) - float(t[0]))
+    if size == 1:
+        return eng.ftle_stencil(local, 0, diag._xf, diag._yf, edge_order, t_span, 0, diag.ydim,
+                                xi_mode)
+    out = torch.zeros(slab.rows_max, diag.xdim, dtype=torch.float64, device=eng.device)
+    xi = None
+    if slab.rows:
+        _, xi = eng.ftle_stencil(local, slab.lo, diag._xf, diag._yf, edge_order, t_span,
+                                 slab.row0, slab.rows, xi_mode, out=out[:slab.rows])
+    field = sharding.gather_rows(out, diag.ydim, size)
+    if xi_mode != nat.XI_NONE:
+        pad = torch.zeros(slab.rows_max, diag.xdim, 2, dtype=torch.float64, device=eng.device)
+        if xi is not None:
+            pad[:slab.rows] = xi
+        xi = sharding.gather_rows(pad, diag.ydim, size)
+    return field, xi
+
+
+class FTLE(LagrangianDiagnostic2D):
+    """Finite-time Lyapunov exponent field of a 2-D flow (R:lagrangian.py:9-78)."""
+
+    def __init__(self, integrator=odeint_wrapper, num_threads: int = 1) -> None:
+        super().__init__(integrator=integrator, num_threads=num_threads)
+
+    def compute(self, x, y, f, t, edge_order: int = 1, **kwargs):
+        """Returns ``np.ma.MaskedArray[ydim, xdim]``; sets ``x, y, xdim, ydim, flow_map,
+        field`` like the reference.  ``kwargs`` (rtol, atol, max_step, first_step) go to the
+        integrator."""
+        local, slab = super().compute(x, y, f, t, **kwargs)
+        field, _ = _ftle_on_device(self, local, slab, t, edge_order, nat.XI_NONE)
+        self.field_device = field
+        self.field = np.ma.MaskedArray(Engine.get().to_host(field))
+        self._collect_stats()
+        return self.field
+
+
+class LCS(LagrangianDiagnostic2D, RidgeExtractor2D):
+    """Lagrangian coherent structures: FTLE ridges (R:lagrangian.py:81-182)."""
+
+    def __init__(self, integrator=odeint_wrapper, num_threads: int = 1) -> None:
+        super().__init__(integrator=integrator, num_threads=num_threads)
+
+    def compute(self, x, y, f, t, edge_order: int = 1, percentile: float = None,
+                force_eigenvectors: bool = False, debug: bool = False, **kwargs):
+        """Returns the list of ridge polylines ``[(n, 2) ndarray, ...]``; sets ``ftle`` and
+        ``lcs`` (and ``Xi_max``, ``directional_derivative``, ``concavity`` when ``debug``)."""
+        local, slab = super().compute(x, y, f, t, **kwargs)
+        xi_mode = nat.XI_FORCED if force_eigenvectors else nat.XI_LAPACK
+        field, xi = _ftle_on_device(self, local, slab, t, edge_order, xi_mode)
+        del self.flow_map  # R:lagrangian.py:137-139
+        eng = Engine.get()
+        self.ftle = np.ma.MaskedArray(eng.to_host(field))
+        self._collect_stats()
+        self.lcs = self.extract_ridges(field, xi, percentile, edge_order, debug)
+        if debug:
+            self.Xi_max = np.ma.MaskedArray(eng.to_host(xi))
+        return self.lcs

@@ -1,0 +1,108 @@
+"""Row-slab sharding of the seed grid over the ranks of one box.
+
+Seeds are independent, so the flow-map kernel shards with no data-path collective.  The
+stencil needs the neighbouring slab's boundary row (central difference): one point-to-point
+exchange of a single row per neighbour (xdim * 16 B), then an all-gather of the output rows.
+Everything here works on CPU tensors with the ``gloo`` backend as well (tests) — it only moves
+rows, it never computes.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+_mode = "auto"  # "auto": shard when torch.distributed is initialised with world_size > 1
+
+
+def set_distributed(mode) -> None:
+    """``True``/``"auto"``: shard across the default process group when it exists;
+    ``False``: every rank computes the whole grid."""
+    global _mode
+    _mode = "auto" if mode in (True, "auto") else "off"
+
+
+def world():
+    """(rank, world_size) the diagnostics shard over."""
+    if _mode != "off" and dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+@dataclass(frozen=True)
+class Slab:
+    """Rows a rank owns and the rows it must hold locally (own + halo)."""
+    row0: int      # first own row (global)
+    rows: int      # number of own rows (0 for idle ranks)
+    lo: int        # first local row (global index)
+    hi: int        # one past the last local row
+    rows_max: int  # largest slab in the partition (gather padding)
+
+    @property
+    def nloc(self) -> int:
+        return self.hi - self.lo
+
+    @property
+    def halo_lo(self) -> int:
+        return self.row0 - self.lo
+
+    @property
+    def halo_hi(self) -> int:
+        return self.hi - (self.row0 + self.rows)
+
+
+def active_ranks(ydim: int, size: int) -> int:
+    """Ranks that get rows: every slab keeps >= 2 rows so a 1-row halo always suffices (the
+    one-sided edge_order=2 formulas touch rows 0..2 / ydim-3..ydim-1 only)."""
+    return max(1, min(size, ydim // 2))
+
+
+def partition(ydim: int, size: int, rank: int) -> Slab:
+    """Balanced contiguous row slabs with a 1-row halo towards each existing neighbour."""
+    n = active_ranks(ydim, size)
+    base, extra = divmod(ydim, n)
+    rows_max = base + (1 if extra else 0)
+    if rank >= n:
+        return Slab(ydim, 0, ydim, ydim, rows_max)
+    row0 = rank * base + min(rank, extra)
+    rows = base + (1 if rank < extra else 0)
+    lo = row0 - 1 if rank > 0 else row0
+    hi = row0 + rows + (1 if rank < n - 1 else 0)
+    return Slab(row0, rows, lo, hi, rows_max)
+
+
+def exchange_halo(local: torch.Tensor, slab: Slab, ydim: int, rank: int, size: int) -> None:
+    """Fill the halo rows of ``local`` ([nloc, ...], own rows already written) from the
+    neighbouring ranks.  One row each way per neighbour."""
+    n = active_ranks(ydim, size)
+    if n == 1 or rank >= n:
+        return
+    ops, keep = [], []
+    first_own, last_own = slab.halo_lo, slab.halo_lo + slab.rows - 1
+    if rank > 0:  # neighbour above (smaller rows)
+        send = local[first_own].contiguous()
+        keep.append(send)
+        ops.append(dist.P2POp(dist.isend, send, rank - 1))
+        ops.append(dist.P2POp(dist.irecv, local[0], rank - 1))
+    if rank < n - 1:
+        send = local[last_own].contiguous()
+        keep.append(send)
+        ops.append(dist.P2POp(dist.isend, send, rank + 1))
+        ops.append(dist.P2POp(dist.irecv, local[slab.nloc - 1], rank + 1))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+def gather_rows(own_padded: torch.Tensor, ydim: int, size: int) -> torch.Tensor:
+    """All-gather per-rank outputs (``[rows_max, ...]``, first ``rows`` valid) into the full
+    ``[ydim, ...]`` array on every rank."""
+    rows_max = own_padded.shape[0]
+    tail = tuple(own_padded.shape[1:])
+    buf = torch.empty((size, rows_max) + tail, dtype=own_padded.dtype, device=own_padded.device)
+    dist.all_gather(list(buf.unbind(0)), own_padded.contiguous())
+    n = active_ranks(ydim, size)
+    if n == size and ydim == size * rows_max:
+        return buf.view((ydim,) + tail)
+    parts = [buf[r, :partition(ydim, size, r).rows] for r in range(n)]
+    return torch.cat(parts, dim=0)

@@ -1,0 +1,183 @@
+/* dynlab_b200 — C-ABI of the B200-native FTLE / Eulerian hot path.
+ *
+ * The reference (hokiepete/dynlab) is pure Python and has no FFI of its own; its
+ * boundary for this path is the Python class API.  These entry points
+ * are what a binding for that path would call — one per reference hot loop — and are
+ * what dynlab_b200's Python host (ctypes, dynlab_b200/_native.py) calls.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative DLB_ERR_*;
+ *     dlb_last_error() gives the message (thread-local).  Nothing throws, nothing owns
+ *     caller memory.
+ *   - pointers named d_* are DEVICE pointers on the current CUDA device; pointers named
+ *     h_* are HOST pointers (coordinate vectors and parameters: O(xdim+ydim) data that the
+ *     library inspects on the host, e.g. numpy's uniform-spacing test).
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  All work is
+ *     enqueued on it; the functions do not synchronise unless stated.
+ *   - all floating point data is IEEE binary64, C order (x fastest).
+ *   - a flow is named by (flow_id, params[]) where params are the Python signature's keyword
+ *     parameters of dynlab.flows.<name> in declaration order (R:src/dynlab/flows.py).
+ */
+#ifndef DYNLAB_B200_H
+#define DYNLAB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLB_ABI_VERSION 1
+
+enum dlb_error {
+  DLB_OK = 0,
+  DLB_ERR_ARG = -1,       /* bad argument (flow id, dimensions, edge_order, null pointer) */
+  DLB_ERR_CUDA = -2,      /* a CUDA runtime call failed */
+  DLB_ERR_TOO_SMALL = -3, /* axis shorter than edge_order+1 (numpy raises ValueError) */
+  DLB_ERR_WORKSPACE = -4  /* workspace too small */
+};
+
+/* R:src/dynlab/flows.py — the 15 analytic flows; ids are stable ABI. */
+enum dlb_flow {
+  DLB_FLOW_DOUBLE_GYRE = 0,             /* flows.py:13-33   params A, w, e */
+  DLB_FLOW_AUTONOMOUS_DOUBLE_GYRE = 1,  /* flows.py:36-48   */
+  DLB_FLOW_BICKLEY_JET = 2,             /* flows.py:51-96   params U0,L,re,A2,A3,c2,c3,k2,k3,scale */
+  DLB_FLOW_GLIDER = 3,                  /* flows.py:99-113  */
+  DLB_FLOW_HILLS_VORTEX = 4,            /* flows.py:116-128 */
+  DLB_FLOW_SIGMOIDAL = 5,               /* flows.py:131-142 */
+  DLB_FLOW_AUTONOMOUS_DUFFING = 6,      /* flows.py:145-157 */
+  DLB_FLOW_DUFFING = 7,                 /* flows.py:160-176 params A, gamma, omega */
+  DLB_FLOW_PENDULUM = 8,                /* flows.py:179-195 params A, gamma, omega */
+  DLB_FLOW_HURRICANE = 9,               /* flows.py:198-221 params eye_alpha, eye_omega, eye_amplitude */
+  DLB_FLOW_VAN_DER_POL = 10,            /* flows.py:224-241 params A, mu, gamma, omega */
+  DLB_FLOW_BEAD = 11,                   /* flows.py:244-262 params epsilon, gamma */
+  DLB_FLOW_LOTKA_VOLTERRA = 12,         /* flows.py:265-284 params alpha, beta, gamma, delta */
+  DLB_FLOW_ABC = 13,                    /* flows.py:287-307 params ABC_Amplitude, A, B, C (3-D) */
+  DLB_FLOW_LORENZ = 14,                 /* flows.py:310-331 params sigma, rho, beta (3-D) */
+  DLB_FLOW_COUNT = 15
+};
+
+/* Eulerian stencil modes (kernel K3). */
+enum dlb_euler_mode {
+  DLB_EULER_S_MIN = 0,  /* AttractionRate: smallest eigenvalue of S   R:eulerian.py:47-59, :90 */
+  DLB_EULER_S_MAX = 1,  /* RepulsionRate: largest eigenvalue of S     R:eulerian.py:120 */
+  DLB_EULER_RATE = 2,   /* TrajectoryRepulsionRate  rho-dot           R:eulerian.py:159-165 */
+  DLB_EULER_RATIO = 3   /* TrajectoryRepulsionRatio nu-dot            R:eulerian.py:167-171 */
+};
+
+/* Eigenvector output conventions (SURVEY §8a "Eigen conventions"). */
+enum dlb_xi_mode {
+  DLB_XI_NONE = 0,
+  DLB_XI_LAPACK = 1, /* sign/order as LAPACK dgeev (np.linalg.eig) returns it */
+  DLB_XI_FORCED = 2  /* then force_eigenvectors2D, R:src/dynlab/utils.py:41-45 */
+};
+
+/* Counters written by the integrator kernels (device array of 8 uint64). */
+enum dlb_counter {
+  DLB_CNT_NFEV = 0,     /* total RHS evaluations = 2*seeds + 6*attempts (scipy's nfev summed) */
+  DLB_CNT_ACCEPTED = 1, /* accepted steps */
+  DLB_CNT_REJECTED = 2, /* rejected attempts */
+  DLB_CNT_FAILED = 3,   /* seeds that ended with scipy status -1 (step size too small) */
+  DLB_CNT_SEEDS = 4,    /* seeds integrated */
+  DLB_CNT_WORDS = 8
+};
+
+int dlb_abi_version(void);
+const char* dlb_last_error(void);
+
+/* Flow registry. */
+int dlb_flow_dim(int flow_id);        /* 2 or 3; <0 if unknown */
+int dlb_flow_nparams(int flow_id);    /* number of keyword parameters */
+const char* dlb_flow_name(int flow_id);
+
+/* Bytes of device workspace the grid entry points need for a (xdim, ydim) grid. */
+size_t dlb_workspace_bytes(int64_t xdim, int64_t ydim);
+
+/* K0 — evaluate a flow on points or on meshgrid(x, y).
+ * Replaces `f(t, np.meshgrid(x, y))` in EulerianDiagnostic2D.compute
+ * (R:src/dynlab/diagnostics/_base_classes.py:101-102).
+ * points: d_px/d_py/d_pz are n-element device arrays (d_pz NULL for 2-D flows).
+ * grid  : point (i, j) = (x[j], y[i]); outputs are [ydim][xdim]. */
+int dlb_flow_eval_points(int flow_id, const double* h_params, int n_params, double t,
+                         const double* d_px, const double* d_py, const double* d_pz, int64_t n,
+                         double* d_u, double* d_v, double* d_w, void* stream);
+int dlb_flow_eval_grid(int flow_id, const double* h_params, int n_params, double t,
+                       const double* h_x, int64_t xdim, const double* h_y, int64_t ydim,
+                       double* d_u, double* d_v, void* d_workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* K1 — flow map of a row slab: for every node (x[j], y[row0+i]), i<rows, the endpoint of the
+ * trajectory integrated from t0 to tf with scipy-RK45 semantics.
+ * Replaces LagrangianDiagnostic2D.compute's seed loop + integrator
+ * (R:src/dynlab/diagnostics/_base_classes.py:175-189, R:src/dynlab/utils.py:6-25 with the
+ * RK45 semantics of scipy/integrate/_ivp/rk.py:14-176, common.py:44-134, base.py:164-210).
+ * d_flow_map: [rows][xdim][2] (Phi_x, Phi_y).  max_step = INFINITY for none; first_step = 0
+ * to select the initial step as scipy does.  Optional per-seed outputs (NULL to skip):
+ * d_nfev [rows][xdim] uint32, d_status [rows][xdim] int8 (0 ok, -1 step size too small).
+ * d_counters: DLB_CNT_WORDS uint64, zeroed by this call. */
+int dlb_flowmap_rk45(int flow_id, const double* h_params, int n_params,
+                     const double* h_x, int64_t xdim, const double* h_y, int64_t row0, int64_t rows,
+                     double t0, double tf, double rtol, double atol, double max_step,
+                     double first_step, double* d_flow_map, uint32_t* d_nfev, int8_t* d_status,
+                     uint64_t* d_counters, void* d_workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* K1 (generic) — endpoints of m seeds of dimension n_dim (2 or 3; must match the flow).
+ * d_seeds/d_out: [m][n_dim].  h_atol: n_dim values.  Same semantics as above; this is the
+ * entry the integrator-protocol wrapper `integrator(f, t, Y0)[-1, :]` maps to
+ * (R:src/dynlab/diagnostics/_base_classes.py:180-182). */
+int dlb_rk45_endpoints(int flow_id, const double* h_params, int n_params, int n_dim,
+                       const double* d_seeds, int64_t m, double t0, double tf, double rtol,
+                       const double* h_atol, double max_step, double first_step, double* d_out,
+                       uint32_t* d_nfev, int8_t* d_status, uint64_t* d_counters,
+                       void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* K2 — FTLE field from a flow map: np.gradient (both branches, edge_order 1|2), Cauchy-Green
+ * tensor, largest eigenvalue, log.  Replaces FTLE.compute / LCS.compute after the flow map
+ * (R:src/dynlab/diagnostics/lagrangian.py:50-78, :130-167; numpy/lib/_function_base_impl.py
+ * :1246-1384).
+ * The caller holds `nloc` consecutive rows of the global [ydim][xdim] grid starting at global
+ * row `grow0` (own rows plus halo rows) in d_flow_map [nloc][xdim][2]; the call produces
+ * global rows [out_row0, out_row0+out_rows) into d_ftle [out_rows][xdim] (and d_xi
+ * [out_rows][xdim][2] when xi_mode != DLB_XI_NONE).  Every row the stencil of an output row
+ * touches must be inside [grow0, grow0+nloc).  t_span = |tf - t0|. */
+int dlb_ftle_stencil(const double* d_flow_map, int64_t nloc, int64_t grow0,
+                     const double* h_x, int64_t xdim, const double* h_y, int64_t ydim,
+                     int edge_order, double t_span, int64_t out_row0, int64_t out_rows,
+                     double* d_ftle, double* d_xi, int xi_mode,
+                     void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* K3 — Eulerian stencil + eigen: velocity gradients, rate-of-strain tensor S and one of the
+ * dlb_euler_mode fields.  Replaces EulerianDiagnostic2D.compute's gradients and the per-point
+ * loops of _AttractionRepulsionRate / _TrajectoryRepulsionRateRatio / iLES
+ * (R:src/dynlab/diagnostics/_base_classes.py:110-111, R:src/dynlab/diagnostics/eulerian.py
+ * :47-59, :159-195, :317-343).  Same slab geometry as dlb_ftle_stencil; d_u/d_v are
+ * [nloc][xdim].  d_mask ([out_rows][xdim] uint8, 1 = masked) is written for RATE/RATIO where
+ * u*u+v*v == 0 (R:eulerian.py:188-192) and may be NULL for the S modes.  `negate` != 0 flips
+ * the sign of the field (iLES kind='attracting', R:eulerian.py:339-340). */
+int dlb_euler_stencil(int mode, const double* d_u, const double* d_v, int64_t nloc, int64_t grow0,
+                      const double* h_x, int64_t xdim, const double* h_y, int64_t ydim,
+                      int edge_order, int64_t out_row0, int64_t out_rows, int negate,
+                      double* d_field, uint8_t* d_mask, double* d_xi, int xi_mode,
+                      void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Ridge field — gradient + Hessian of a scalar field, directional derivative
+ * grad(f).xi and concavity xi^T H xi, with the reference's masks (field <= 0, concavity >= 0,
+ * field <= threshold when use_threshold).  Replaces RidgeExtractor2D.extract_ridges up to the
+ * contour call (R:src/dynlab/diagnostics/_base_classes.py:216-268).  Whole grid on one device:
+ * d_field [ydim][xdim], d_xi [ydim][xdim][2] -> d_dd, d_conc [ydim][xdim], d_mask uint8.
+ * d_scratch: 2*ydim*xdim doubles (first derivatives). */
+int dlb_ridge_field(const double* d_field, const double* d_xi, const double* h_x, int64_t xdim,
+                    const double* h_y, int64_t ydim, int edge_order, int use_threshold,
+                    double threshold, double* d_dd, double* d_conc, uint8_t* d_mask,
+                    double* d_scratch, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* FP64 roofline denominator: runs a register-resident DFMA chain kernel and returns the
+ * sustained FP64 throughput in FLOP/s (FMA = 2) through *flops_per_s.  Synchronises. */
+int dlb_dfma_peak(int iters, double* flops_per_s, double* elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNLAB_B200_H */

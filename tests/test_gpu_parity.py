@@ -1,0 +1,443 @@
+"""GPU parity tests proper: the CUDA path (through the public API and the C-ABI) against
+(1) the reference's own known-answer vectors, (2) fixtures generated from the unmodified
+reference (tests/golden/), (3) the oracle on the same seeded inputs.
+
+Tolerances (north_star): flow-map endpoints within 10*rtol relative (floor: atol-scale),
+FTLE within 1e-6 relative.  Measured agreement is orders of magnitude tighter and the tests
+assert the tighter figures where the arithmetic allows (stencil/eigen kernels: 1e-11).
+"""
+import functools
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle.make_golden import FTLE_CASES
+from tests import reference_vectors as rv
+from tests.test_oracle_golden import EUL_CASES, EUL_GRIDS
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def dl():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import dynlab_b200
+    from dynlab_b200 import diagnostics, flows, utils  # noqa: F401
+
+    return dynlab_b200
+
+
+def rel_err(a, b, floor):
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+# ---------------------------------------------------------------- K0 / flows
+def test_flows_reference_vectors(dl):
+    """R:tests/test_flows.py through the device twins (K0, grid mode)."""
+    from dynlab_b200._engine import Engine
+    from dynlab_b200._resolve import resolve_flow
+
+    eng = Engine.get()
+    for name, (ue, ve) in rv.FLOWS_2D.items():
+        _, fid, _, params = resolve_flow(getattr(dl.flows, name))
+        u, v = eng.flow_eval_grid(fid, params, 0.0, np.array([0., 1., 2.]), np.array([0., 1.]))
+        assert np.allclose(ue, u.cpu().numpy()), name
+        assert np.allclose(ve, v.cpu().numpy()), name
+    X, Y, Z = np.meshgrid([0, 1], [0, 1], [0, 1])
+    pts = torch.tensor(np.stack([X.ravel(), Y.ravel(), Z.ravel()]), dtype=torch.float64, device=eng.device)
+    for name, exp in rv.FLOWS_3D.items():
+        _, fid, dim, params = resolve_flow(getattr(dl.flows, name))
+        out = eng.flow_eval_points(fid, dim, params, 0.0, pts).cpu().numpy()
+        for k in range(3):
+            assert np.allclose(np.array(exp[k]).ravel(), out[k]), name
+
+
+def test_flows_golden_points(dl, golden):
+    """All 15 device twins on 257 random points x 4 times vs the reference's numpy output."""
+    from dynlab_b200._engine import Engine
+    from dynlab_b200._resolve import resolve_flow
+
+    g = golden("flows")
+    eng = Engine.get()
+    for name, (fid, dim, _) in dl.flows.FLOW_REGISTRY.items():
+        P = (g["pts3"] if dim == 3 else g["pts2"]) * (2000.0 if name == "bickley_jet" else 1.0)
+        pts = torch.tensor(P, dtype=torch.float64, device=eng.device)
+        _, fid, dim, params = resolve_flow(getattr(dl.flows, name))
+        for k, t in enumerate(g["ts"]):
+            out = eng.flow_eval_points(fid, dim, params, float(t), pts).cpu().numpy()
+            ref = g[name][k]
+            scale = np.abs(ref).max()
+            assert np.abs(out - ref).max() <= 4e-15 * scale + 1e-300, (name, t)
+    _, fid, dim, params = resolve_flow(functools.partial(dl.flows.double_gyre, A=0.25, w=1.3, e=0.1))
+    pts = torch.tensor(g["pts2"], dtype=torch.float64, device=eng.device)
+    out = eng.flow_eval_points(fid, dim, params, 0.7, pts).cpu().numpy()
+    assert np.abs(out - g["double_gyre_params"]).max() < 1e-15
+    _, fid, dim, params = resolve_flow(dl.flows.FlowSpec("bickley_jet", scale=4000.0))
+    out = eng.flow_eval_points(fid, dim, params, 0.01, pts).cpu().numpy()
+    assert np.abs(out - g["bickley_scaled"]).max() < 1e-14 * np.abs(g["bickley_scaled"]).max()
+
+
+def test_device_trig_accuracy(dl):
+    """dm::sin / dm::sincos (csrc/dmath.cuh) against numpy over small, large and
+    near-multiple-of-pi arguments, through pendulum (v = -sin x) and abc (sin/cos of x,y,z)."""
+    from dynlab_b200._engine import Engine
+    from dynlab_b200._resolve import resolve_flow
+
+    eng = Engine.get()
+    rng = np.random.default_rng(7)
+    k = np.arange(-200, 200)
+    xs = np.concatenate([
+        rng.uniform(-10, 10, 4000), rng.uniform(-1e5, 1e5, 4000), rng.uniform(-1e9, 1e9, 1000),
+        k * (np.pi / 2), k * (np.pi / 2) + 1e-9, np.nextafter(k * np.pi, np.inf),
+        [0.0, -0.0, 1e-300, 5e-324, 105614.9, 105615.1]])
+    _, fid, dim, params = resolve_flow(functools.partial(dl.flows.pendulum, A=0.0, gamma=0.0))
+    pts = torch.tensor(np.stack([xs, np.zeros_like(xs)]), dtype=torch.float64, device=eng.device)
+    out = eng.flow_eval_points(fid, dim, params, 0.0, pts).cpu().numpy()
+    ref = -np.sin(xs)
+    ulp = np.spacing(np.abs(ref))
+    assert (np.abs(out[1] - ref) <= 2 * ulp + 1e-300).all()
+    _, fid, dim, params = resolve_flow(functools.partial(dl.flows.abc, A=1.0, B=0.0, C=0.0))
+    p3 = torch.tensor(np.stack([xs, xs, xs]), dtype=torch.float64, device=eng.device)
+    out = eng.flow_eval_points(fid, dim, params, 0.0, p3).cpu().numpy()
+    for got, ref in ((out[0], np.sin(xs)), (out[1], np.cos(xs))):
+        assert (np.abs(got - ref) <= 2 * np.spacing(np.abs(ref)) + 1e-300).all()
+
+
+# ---------------------------------------------------------------- reference's own tests
+def test_reference_test_ftle(dl):
+    """R:tests/test_diagnostics/test_lagrangian.py:6-17, verbatim inputs, default integrator."""
+    f = dl.diagnostics.FTLE(num_threads=1).compute(rv.FTLE_X, rv.FTLE_Y, dl.flows.double_gyre, rv.FTLE_T)
+    assert isinstance(f, np.ma.MaskedArray) and f.shape == (2, 3)
+    assert np.allclose(rv.FTLE_EXPECTED, f)
+    assert f[0, 2] == 0 and f[1, 0] == 0  # lambda_max < 1 clamp
+
+
+def test_reference_test_eulerian(dl):
+    """R:tests/test_diagnostics/test_eulerian.py:8-123 (8 tests), verbatim inputs."""
+    D, dg = dl.diagnostics, dl.flows.double_gyre
+    u, v = dg(0, np.meshgrid(rv.EUL_X, rv.EUL_Y))
+    for kw in (dict(f=dg, t=0), dict(u=u, v=v)):
+        assert np.allclose(rv.ATTRACTION_EXPECTED, D.AttractionRate().compute(rv.EUL_X, rv.EUL_Y, **kw))
+        assert np.allclose(rv.REPULSION_EXPECTED, D.RepulsionRate().compute(rv.EUL_X, rv.EUL_Y, **kw))
+    u, v = dg(0, np.meshgrid(rv.TRAJ_X, rv.TRAJ_Y))
+    for kw in (dict(f=dg, t=0), dict(u=u, v=v)):
+        assert np.allclose(rv.RHODOT_EXPECTED, D.TrajectoryRepulsionRate().compute(rv.TRAJ_X, rv.TRAJ_Y, **kw))
+        assert np.allclose(rv.NUDOT_EXPECTED, D.TrajectoryRepulsionRatio().compute(rv.TRAJ_X, rv.TRAJ_Y, **kw))
+
+
+# ---------------------------------------------------------------- K1 + K2, config 1
+def test_ftle_c1_against_reference(dl, golden):
+    """BASELINE config 1 in full (R:README.md:24-26) vs the unmodified reference (RK45)."""
+    g = golden("ftle_c1")
+    d = dl.diagnostics.FTLE(num_threads=1)
+    nf = torch.zeros(101, 101, dtype=torch.int32, device="cuda")
+    field = d.compute(g["x"], g["y"], dl.flows.double_gyre, (10, 0), edge_order=2, rtol=1e-8, atol=1e-8)
+    rtol = 1e-8
+    e = rel_err(d.flow_map, g["flow_map"], 1.0)
+    assert e.max() < 10 * rtol, e.max()          # north_star bar
+    assert e.max() < 1e-10, e.max()               # what the arithmetic actually gives
+    ef = rel_err(np.ma.getdata(field), g["field"], 1e-3)
+    excluded = (ef > 1e-6).mean()
+    assert excluded == 0.0                        # no ridge-cusp exclusions needed
+    assert ef.max() < 1e-8, ef.max()
+    assert d.stats["nfev"] == int(g["nfev"].sum())  # identical step sequences in total
+    assert d.stats["failed"] == 0 and d.stats["seeds"] == 101 * 101
+
+
+def test_flow_map_per_seed_nfev(dl, golden):
+    """Per-seed nfev of K1 equals scipy's on every seed of config 1."""
+    from dynlab_b200._engine import Engine
+    from dynlab_b200._resolve import resolve_flow
+
+    g = golden("ftle_c1")
+    eng = Engine.get()
+    _, fid, _, params = resolve_flow(dl.flows.double_gyre)
+    nfev = torch.zeros(101, 101, dtype=torch.int32, device=eng.device)
+    status = torch.full((101, 101), 7, dtype=torch.int8, device=eng.device)
+    fm = eng.flow_map(fid, params, g["x"], g["y"], 0, 101, 10.0, 0.0, 1e-8, 1e-8, nfev=nfev, status=status)
+    assert np.array_equal(nfev.cpu().numpy(), g["nfev"])
+    assert (status.cpu().numpy() == 0).all()
+    assert np.abs(fm.cpu().numpy() - g["flow_map"]).max() < 1e-10
+
+
+@pytest.mark.parametrize("name", list(FTLE_CASES))
+def test_ftle_cases_against_reference(dl, golden, name):
+    """Every 2-D flow, both time directions, uniform / non-uniform / mixed grids, edge_order
+    1 and 2, loose and tight tolerances — vs fixtures from the unmodified reference."""
+    g = golden("ftle_cases")
+    fl, kw, x, y, t, eo, tol = FTLE_CASES[name]
+    atol = tol if name != "dg_loose" else 1e-6
+    f = getattr(dl.flows, fl)
+    if kw:
+        f = functools.partial(f, **kw)
+    d = dl.diagnostics.FTLE()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        field = d.compute(x, y, f, t, edge_order=eo, rtol=tol, atol=atol)
+    ref_fm, ref_f, st = g[name + "__flow_map"], g[name + "__field"], g[name + "__status"]
+    ok = st == 0
+    assert d.stats["failed"] == int((~ok).sum())
+    assert bool(w) == bool((~ok).any())  # RuntimeWarning iff scipy reported status -1 seeds
+    e = rel_err(d.flow_map, ref_fm, 1.0)[ok]
+    assert e.max() < 10 * tol, (name, e.max())
+    if tol <= 1e-8:
+        assert e.max() < 1e-9, (name, e.max())
+    # FTLE: compare where all stencil inputs are regular seeds
+    if ok.all():
+        ef = rel_err(np.ma.getdata(field), ref_f, 1e-3)
+        assert ef.max() < (1e-6 if tol <= 1e-8 else 1e-2), (name, ef.max())
+    assert d.stats["nfev"] >= int(g[name + "__nfev"][ok].sum())
+
+
+def test_ftle_stencil_alone(dl, golden):
+    """K2 on the reference's own flow maps: np.gradient both branches, both edge orders."""
+    from dynlab_b200._engine import Engine
+
+    eng = Engine.get()
+    g = golden("ftle_cases")
+    for name, (fl, kw, x, y, t, eo, tol) in FTLE_CASES.items():
+        if name in ("glider_blowup",):
+            continue
+        fm = torch.tensor(g[name + "__flow_map"], device=eng.device)
+        x64, y64 = np.ascontiguousarray(x, dtype=float), np.ascontiguousarray(y, dtype=float)
+        out, _ = eng.ftle_stencil(fm, 0, x64, y64, eo, abs(t[1] - t[0]), 0, len(y))
+        ref = g[name + "__field"]
+        # gradient cancellation noise: eps * |f| / dx relative to the gradient scale
+        assert rel_err(out.cpu().numpy(), ref, 1e-3).max() < 1e-11, name
+    gc = golden("ftle_c1")
+    fm = torch.tensor(gc["flow_map"], device=eng.device)
+    out, _ = eng.ftle_stencil(fm, 0, gc["x"], gc["y"], 2, 10.0, 0, 101)
+    assert rel_err(out.cpu().numpy(), gc["field"], 1e-3).max() < 1e-11
+
+
+def test_stencil_slabs_match_full_grid(dl, golden):
+    """Row-slab geometry of the C-ABI (grow0 / nloc / halo): any partition gives the bits of
+    the single-slab result (this is what each rank runs in the multi-GPU path)."""
+    from dynlab_b200 import sharding
+    from dynlab_b200._engine import Engine
+
+    eng = Engine.get()
+    gc = golden("ftle_c1")
+    fm = torch.tensor(gc["flow_map"], device=eng.device)
+    x, y = gc["x"], gc["y"]
+    for eo in (1, 2):
+        full, xi_full = eng.ftle_stencil(fm, 0, x, y, eo, 10.0, 0, 101, xi_mode=1)
+        for size in (2, 3, 8, 64):
+            parts, xis = [], []
+            for r in range(size):
+                s = sharding.partition(101, size, r)
+                if not s.rows:
+                    continue
+                o, xi = eng.ftle_stencil(fm[s.lo:s.hi].contiguous(), s.lo, x, y, eo, 10.0, s.row0, s.rows, xi_mode=1)
+                parts.append(o)
+                xis.append(xi)
+            assert torch.equal(torch.cat(parts), full)
+            assert torch.equal(torch.cat(xis), xi_full)
+
+
+# ---------------------------------------------------------------- K3 / ridge field
+@pytest.mark.parametrize("name", EUL_CASES)
+def test_eulerian_against_reference(dl, golden, name):
+    g = golden("eulerian")
+    D = dl.diagnostics
+    x, y, eo = EUL_GRIDS[name]
+    u, v = g[name + "__u"], g[name + "__v"]
+    gs = max(np.abs(u).max(), np.abs(v).max()) / min(np.diff(x).min(), np.diff(y).min())  # gradient scale
+
+    def close(a, b, tol=1e-12):
+        assert np.abs(a - b).max() <= tol * gs, (name, np.abs(a - b).max(), gs)
+
+    close(np.ma.getdata(D.AttractionRate().compute(x, y, u=u, v=v, edge_order=eo)), g[name + "__att"])
+    close(np.ma.getdata(D.RepulsionRate().compute(x, y, u=u, v=v, edge_order=eo)), g[name + "__rep"])
+    for key, cls in (("rate", D.TrajectoryRepulsionRate), ("ratio", D.TrajectoryRepulsionRatio)):
+        r = cls().compute(x, y, u=u, v=v, edge_order=eo)
+        mask = g[f"{name}__{key}_mask"]
+        assert np.array_equal(np.ma.getmaskarray(r), mask)
+        close(np.ma.getdata(r)[~mask], g[f"{name}__{key}"][~mask], 4e-12)
+    for kind in ("attracting", "repelling"):
+        for forced in (True, False):
+            tag = f"{name}__iles_{kind}_{'forced' if forced else 'raw'}"
+            il = D.iLES()
+            il.compute(x, y, u=u, v=v, kind=kind, edge_order=eo, percentile=60,
+                       force_eigenvectors=forced, debug=True)
+            close(np.ma.getdata(il.field), g[tag + "__field"])
+            xi_ref = g[tag + "__xi"]
+            xi = np.ma.getdata(il.Xi_max)
+            # eigenvectors: same sign convention as LAPACK; compare where the eigenvalues are
+            # separated (degenerate S has no unique eigenvector)
+            sep = np.abs(g[name + "__rep"] - g[name + "__att"]) > 1e-9 * gs
+            assert np.abs(xi - xi_ref)[sep].max() < 1e-7, (tag, np.abs(xi - xi_ref)[sep].max())
+            frac_sign_ok = (np.sum(xi * xi_ref, axis=-1)[sep] > 0).mean()
+            assert frac_sign_ok == 1.0, (tag, frac_sign_ok)
+
+
+def test_eulerian_function_route_matches_velocity_route(dl):
+    """f,t route (K0 on the device) == u,v route (host arrays uploaded)."""
+    D, fl = dl.diagnostics, dl.flows
+    x, y = np.linspace(0, 20000, 300), np.linspace(-4000, 4000, 200)
+    u, v = fl.bickley_jet(0.25, np.meshgrid(x, y))
+    a = D.AttractionRate().compute(x, y, u=u, v=v, edge_order=2)
+    d = D.AttractionRate()
+    b = d.compute(x, y, f=fl.bickley_jet, t=0.25, edge_order=2)
+    gs = np.abs(u).max() / np.diff(x).min()
+    assert np.abs(a - b).max() < 1e-12 * gs
+    assert np.abs(d.u - u).max() < 1e-11 * np.abs(u).max()  # lazily downloaded K0 output
+
+
+@pytest.mark.parametrize("name,x,y,t,eo,pct", [
+    ("dg_lcs", np.linspace(0, 2, 20), np.linspace(0, 1, 10), (0.1, 0), 1, None),
+    ("dg_lcs_p80", np.linspace(0, 2, 41), np.linspace(0, 1, 21), (10, 0), 2, 80)])
+def test_lcs_fields_against_reference(dl, golden, name, x, y, t, eo, pct):
+    """LCS: FTLE, Xi_max (LAPACK sign, raw and forced), ridge field and its masks."""
+    g = golden("lcs")
+    for forced in (False, True):
+        tag = f"{name}_{'forced' if forced else 'raw'}"
+        l = dl.diagnostics.LCS()
+        lines = l.compute(x, y, f=dl.flows.double_gyre, t=t, edge_order=eo, percentile=pct,
+                          force_eigenvectors=forced, debug=True, rtol=1e-8, atol=1e-8)
+        assert isinstance(lines, list)
+        assert rel_err(np.ma.getdata(l.ftle), g[tag + "__ftle"], 1e-3).max() < 1e-7
+        xi, xi_ref = np.ma.getdata(l.Xi_max), g[tag + "__xi"]
+        assert (np.sum(xi * xi_ref, axis=-1) > 0).all()
+        assert np.abs(xi - xi_ref).max() < 1e-6
+        dd_ref, m_ref = g[tag + "__dd"], g[tag + "__dd_mask"]
+        m = np.ma.getmaskarray(l.directional_derivative)
+        assert (m != m_ref).mean() <= 0.01  # masks may differ where concavity ~ 0 to rounding
+        both = ~m & ~m_ref
+        sc = np.nanmax(np.abs(dd_ref))
+        assert np.abs(np.ma.getdata(l.directional_derivative) - dd_ref)[both].max() < 1e-6 * sc
+
+
+# ---------------------------------------------------------------- errors / edge cases
+def test_error_paths(dl):
+    D, fl = dl.diagnostics, dl.flows
+    x, y = np.linspace(0, 2, 5), np.linspace(0, 1, 4)
+    with pytest.raises(ValueError):
+        D.FTLE(num_threads=0)
+    with pytest.raises(ValueError):
+        D.FTLE().compute(x, y, fl.double_gyre, (0, 1, 2))
+    with pytest.raises(ValueError):
+        D.FTLE().compute(np.zeros((2, 2)), y, fl.double_gyre, (0, 1))
+    with pytest.raises(ValueError):
+        D.FTLE().compute(x, y, fl.double_gyre, (0, 1), edge_order=3)
+    with pytest.raises(ValueError):  # numpy: axis shorter than edge_order + 1
+        D.FTLE().compute([0.0, 1.0], y, fl.double_gyre, (0, 1), edge_order=2)
+    with pytest.raises(NotImplementedError):  # no device twin, no CPU fallback
+        D.FTLE().compute(x, y, lambda t, Y: (Y[1], -Y[0]), (0, 1))
+    with pytest.raises(NotImplementedError):  # foreign integrator
+        D.FTLE(integrator=lambda f, t, Y: None).compute(x, y, fl.double_gyre, (0, 1))
+    with pytest.raises(TypeError):
+        D.FTLE().compute(x, y, fl.double_gyre, (0, 1), hmax=0.1)
+    with pytest.raises(RuntimeError):
+        D.AttractionRate().compute(x, y)
+    with pytest.raises(ValueError):
+        D.AttractionRate().compute(x, y, u=np.zeros(5), v=np.zeros(5))
+    with pytest.raises(ValueError):
+        D.iLES().compute(x, y, f=fl.double_gyre, t=0)  # default kind='attacting' (reference typo)
+    with pytest.raises(ValueError):
+        D.TrajectoryRepulsionRate.__mro__[1]().compute(x, y, f=fl.double_gyre, t=0, rate_or_ratio="x")
+
+
+def test_small_and_degenerate_grids(dl):
+    """2x2 (edge_order 1), 3x3 (edge_order 2), T == 0, integer coordinates."""
+    from oracle import py_oracle as po
+
+    D, fl = dl.diagnostics, dl.flows
+    for (nx, ny, eo) in ((2, 2, 1), (3, 3, 2), (2, 5, 1), (7, 3, 2)):
+        x, y = np.linspace(0.1, 1.9, nx), np.linspace(0.1, 0.9, ny)
+        d = D.FTLE()
+        f = d.compute(x, y, fl.double_gyre, (0, 3), edge_order=eo, rtol=1e-8, atol=1e-8)
+        fm = po.flow_map(x, y, po.flow("double_gyre"), (0, 3), rtol=1e-8, atol=1e-8)
+        ref = po.ftle_from_flow_map(fm, x, y, (0, 3), eo)
+        assert np.abs(d.flow_map - fm).max() < 1e-10
+        assert np.abs(np.ma.getdata(f) - np.ma.getdata(ref)).max() < 1e-8
+    # integer coordinates (np.gradient casts to float64)
+    d = D.FTLE()
+    f = d.compute([0, 1, 2], [0, 1], fl.double_gyre, (2, 0))
+    assert d.x.dtype.kind == "i" and np.allclose(rv.FTLE_EXPECTED, f)
+
+
+def test_single_trajectory_wrappers(dl):
+    """utils.odeint_wrapper / rk45_wrapper keep the integrator protocol (R:utils.py:6-25)."""
+    from oracle import py_oracle as po
+
+    tr = dl.utils.rk45_wrapper(dl.flows.lorenz, (0, 1.5), (1.0, 2.0, 3.0), rtol=1e-9, atol=1e-9)
+    ref = po.rk45_wrapper(po.flow("lorenz"), (0, 1.5), (1.0, 2.0, 3.0), rtol=1e-9, atol=1e-9)
+    assert tr.shape == (2, 3) and np.array_equal(tr[0], [1.0, 2.0, 3.0])
+    assert np.abs(tr[-1] - ref[-1]).max() < 1e-9
+    tr = dl.utils.odeint_wrapper(dl.flows.abc, (2.0, 0.0), (0.3, 0.2, 0.1))
+    ref = po.rk45_wrapper(po.flow("abc"), (2.0, 0.0), (0.3, 0.2, 0.1), rtol=1.49012e-8, atol=1.49012e-8)
+    assert np.abs(tr[-1] - ref[-1]).max() < 1e-10
+
+
+# ---------------------------------------------------------------- full BASELINE sizes
+def test_ftle_c3_full_size_properties(dl):
+    """BASELINE config 3 (8192x4096, T=10, tol 1e-8) at full size:
+    (a) a strided sample of seeds equals the C oracle's endpoints and nfev;
+    (b) FTLE rows recomputed by the oracle on a patch agree;
+    (c) the double gyre's symmetry (x, y) -> (2 - x, 1 - y) holds across the whole field."""
+    from oracle import c_oracle as co
+    from oracle import py_oracle as po
+
+    x, y = np.linspace(0, 2, 8192), np.linspace(0, 1, 4096)
+    d = dl.diagnostics.FTLE()
+    field = np.ma.getdata(d.compute(x, y, dl.flows.double_gyre, (10, 0), edge_order=2, rtol=1e-8, atol=1e-8))
+    assert field.shape == (4096, 8192) and np.isfinite(field).all()
+    assert d.stats["seeds"] == 8192 * 4096 and d.stats["failed"] == 0
+    fm = d.flow_map
+    p = po.flow_params("double_gyre")
+    # (a) every 64th row / column: 128 x 64 seeds
+    ref, nfev, st = co.flow_map("double_gyre", p, x[::64], y[::64], 10.0, 0.0, 1e-8, 1e-8)
+    assert np.abs(fm[::64, ::64] - ref).max() < 1e-10
+    # (b) a 48 x 48 patch in the interior and the four corners (edge formulas)
+    for (i0, j0) in ((2000, 4000), (0, 0), (4096 - 48, 8192 - 48), (0, 8192 - 48), (4096 - 48, 0)):
+        ys, xs = y[i0:i0 + 48], x[j0:j0 + 48]
+        pf, _, _ = co.flow_map("double_gyre", p, xs, ys, 10.0, 0.0, 1e-8, 1e-8)
+        assert np.abs(fm[i0:i0 + 48, j0:j0 + 48] - pf).max() < 1e-10
+    # stencil on the GPU flow map vs numpy on the same flow map, three row bands incl. edges
+    for sl in (slice(0, 64), slice(2016, 2080), slice(4032, 4096)):
+        lo, hi = max(sl.start - 2, 0), min(sl.stop + 2, 4096)
+        ref_rows = po.ftle_from_flow_map(fm[lo:hi], x, y[lo:hi], (10, 0), 2)
+        a = field[sl]
+        b = np.ma.getdata(ref_rows)[sl.start - lo: sl.start - lo + 64]
+        if sl.start > 0 and sl.stop < 4096:
+            assert rel_err(a, b, 1e-3).max() < 1e-8  # cancellation noise eps*|f|/dx at dx=2.4e-4
+        else:  # band touches a global edge: rows next to lo/hi cut use a different stencil
+            inner = slice(0, 62) if sl.start == 0 else slice(2, 64)
+            assert rel_err(a[inner], b[inner], 1e-3).max() < 1e-8
+    # (c) symmetry: Phi(2-x, 1-y) = (2, 1) - Phi(x, y)  =>  ftle[i, j] == ftle[-1-i, -1-j]
+    sym = np.abs(fm + fm[::-1, ::-1] - np.array([2.0, 1.0]))
+    assert sym.max() < 1e-9, sym.max()
+    rot = field[::-1, ::-1]
+    big = np.abs(field - rot) > 1e-6 * np.maximum(field, 1e-3)
+    assert big.mean() < 1e-4, big.mean()
+
+
+def test_eulerian_c2_full_size_properties(dl):
+    """BASELINE config 2 (8192x8192 bickley_jet, edge_order 2): crops vs the oracle; and
+    attraction + repulsion = trace(S) = du/dx + dv/dy = 0 for this (divergence-free) jet."""
+    from oracle import py_oracle as po
+
+    D, fl = dl.diagnostics, dl.flows
+    x, y = np.linspace(0, 20000, 8192), np.linspace(-4000, 4000, 8192)
+    a = D.AttractionRate()
+    att = np.ma.getdata(a.compute(x, y, f=fl.bickley_jet, t=0.0, edge_order=2))
+    rep = np.ma.getdata(D.RepulsionRate().compute(x, y, f=fl.bickley_jet, t=0.0, edge_order=2))
+    assert att.shape == (8192, 8192) and (att <= rep).all()
+    u, v = a.u, a.v
+    gs = np.abs(u).max() / (x[1] - x[0])
+    for (i0, j0) in ((0, 0), (4000, 3000), (8192 - 40, 8192 - 40)):
+        sl = (slice(i0, i0 + 40), slice(j0, j0 + 40))
+        uo, vo = po.flow("bickley_jet")(0.0, np.meshgrid(x[sl[1]], y[sl[0]]))
+        assert np.abs(u[sl] - uo).max() < 1e-11 * np.abs(u).max()
+        ref = po.attraction_repulsion_rate(x[sl[1]], y[sl[0]], u=u[sl], v=v[sl], edge_order=2)
+        inner = (slice(1, -1), slice(1, -1)) if 0 < i0 < 8000 else (
+            (slice(0, -1), slice(0, -1)) if i0 == 0 else (slice(1, None), slice(1, None)))
+        assert np.abs(att[sl][inner] - np.ma.getdata(ref)[inner]).max() < 1e-11 * gs
+    # trace identity (second-order stencil of a smooth divergence-free field: small, not zero)
+    tr = att + rep
+    assert np.abs(tr).max() < 1e-3 * np.abs(rep).max()

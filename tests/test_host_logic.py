@@ -1,0 +1,235 @@
+"""CPU tests: host logic of the drop-in layer, the C-ABI surface, and the N>1 sharding path
+(world_size 2 and 3, gloo) — no kernel launches."""
+import ctypes
+import functools
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests import reference_vectors as rv
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ C-ABI surface
+def test_library_exports_every_declared_symbol():
+    from dynlab_b200 import _native
+
+    header = open(os.path.join(ROOT, "include", "dynlab_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(dlb_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/dynlab_b200.h but not exported"
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    assert _native.lib.dlb_abi_version() == 1
+
+
+def test_flow_registry_matches_abi():
+    from dynlab_b200 import _native, flows
+
+    assert len(flows.FLOW_REGISTRY) == 15
+    for name, (fid, dim, pnames) in flows.FLOW_REGISTRY.items():
+        assert _native.lib.dlb_flow_name(fid).decode() == name
+        assert _native.lib.dlb_flow_dim(fid) == dim
+        assert _native.lib.dlb_flow_nparams(fid) == len(pnames)
+    assert _native.lib.dlb_flow_dim(99) < 0
+    assert _native.lib.dlb_workspace_bytes(8192, 4096) >= 8 * 4 * (8192 + 4096)
+
+
+def test_abi_argument_errors_without_gpu():
+    """Argument validation happens before any CUDA call."""
+    from dynlab_b200 import _native as nat
+
+    p = nat.darray([0.1, 0.2])
+    x = np.linspace(0, 1, 4)
+    rc = nat.lib.dlb_flowmap_rk45(0, p, 2, nat.dptr(x), 4, nat.dptr(x), 0, 4, 0.0, 1.0, 1e-6, 1e-6,
+                                  np.inf, 0.0, 8, None, None, 8, 8, 1 << 20, None)
+    assert rc == nat.DLB_ERR_ARG and b"parameter count" in nat.lib.dlb_last_error()
+    with pytest.raises(ValueError):
+        nat.check(rc)
+    rc = nat.lib.dlb_ftle_stencil(8, 4, 0, nat.dptr(x), 4, nat.dptr(x), 4, 3, 1.0, 0, 4, 8, None, 0,
+                                  8, 1 << 20, None)
+    assert rc == nat.DLB_ERR_ARG and b"edge_order" in nat.lib.dlb_last_error()
+    rc = nat.lib.dlb_ftle_stencil(8, 2, 0, nat.dptr(x), 2, nat.dptr(x), 2, 2, 1.0, 0, 2, 8, None, 0,
+                                  8, 1 << 20, None)
+    assert rc == nat.DLB_ERR_TOO_SMALL
+
+
+# ------------------------------------------------------------------ flows / resolver / utils
+def test_host_flows_reference_vectors():
+    from dynlab_b200 import flows
+
+    x, y = np.meshgrid([0, 1, 2], [0, 1])
+    for name, (ue, ve) in rv.FLOWS_2D.items():
+        u, v = getattr(flows, name)(0, (x, y))
+        assert np.allclose(ue, u) and np.allclose(ve, v), name
+    X = np.meshgrid([0, 1], [0, 1], [0, 1])
+    for name, exp in rv.FLOWS_3D.items():
+        for e, o in zip(exp, getattr(flows, name)(0, X)):
+            assert np.allclose(e, o), name
+
+
+def test_host_flows_golden(golden):
+    from dynlab_b200 import flows
+
+    g = golden("flows")
+    for n, (_, dim, _) in flows.FLOW_REGISTRY.items():
+        P = (g["pts3"] if dim == 3 else g["pts2"]) * (2000.0 if n == "bickley_jet" else 1.0)
+        for k, t in enumerate(g["ts"]):
+            out = np.stack(np.broadcast_arrays(*getattr(flows, n)(t, tuple(P))))
+            assert np.array_equal(out, g[n][k]), n
+
+
+def test_resolver():
+    from dynlab_b200 import flows
+    from dynlab_b200._resolve import UnsupportedFlowError, resolve_flow
+
+    assert resolve_flow(flows.double_gyre) == ("double_gyre", 0, 2, [0.1, 0.2 * np.pi, 0.25])
+    p = functools.partial(functools.partial(flows.double_gyre, A=0.3), e=0.5)
+    assert resolve_flow(p)[3] == [0.3, 0.2 * np.pi, 0.5]
+    assert resolve_flow(flows.FlowSpec("lorenz", rho=30.0)) == ("lorenz", 14, 3, [10.0, 30.0, 8.0 / 3.0])
+    with pytest.raises(UnsupportedFlowError):
+        resolve_flow(lambda t, Y: (Y[1], -Y[0]))
+    with pytest.raises(UnsupportedFlowError):
+        resolve_flow(functools.partial(flows.double_gyre, 0.0))
+    with pytest.raises(TypeError):
+        resolve_flow(functools.partial(flows.double_gyre, B=1.0))
+    with pytest.raises(TypeError):
+        flows.FlowSpec("double_gyre", B=1.0)
+
+    # a function living in a module called dynlab.flows with the reference's signature
+    ns = {}
+    exec("def pendulum(t, Y, A=0.25, gamma=0.0, omega=1.0):\n    return Y[1], 0*Y[0]\n", ns)
+    f = ns["pendulum"]
+    f.__module__ = "dynlab.flows"
+    assert resolve_flow(f) == ("pendulum", 8, 2, [0.25, 0.0, 1.0])
+
+
+def test_force_eigenvectors_reference_vectors():
+    from dynlab_b200.utils import force_eigenvectors2D
+
+    for a, e in rv.FORCE_EIG:
+        assert (np.array([[e]]) == force_eigenvectors2D(np.array([[a]]))).all()
+
+
+def test_integrator_kwargs():
+    from dynlab_b200.utils import parse_integrator_kwargs
+
+    kw = parse_integrator_kwargs(dict(rtol=1e-8), 1e-3, 1e-6)
+    assert kw["rtol"] == 1e-8 and kw["atol"] == 1e-6 and kw["max_step"] == np.inf
+    with pytest.raises(TypeError):
+        parse_integrator_kwargs(dict(hmax=1.0), 1e-3, 1e-6)
+    with pytest.raises(ValueError):
+        parse_integrator_kwargs(dict(max_step=0.0), 1e-3, 1e-6)
+    with pytest.raises(NotImplementedError):
+        parse_integrator_kwargs(dict(method="LSODA"), 1e-3, 1e-6)
+
+
+def test_constructor_and_validation_without_gpu():
+    from dynlab_b200 import diagnostics as D
+
+    with pytest.raises(ValueError):
+        D.FTLE(num_threads=0)
+    with pytest.raises(ValueError):
+        D.LCS(num_threads=-1)
+    assert D.FTLE(num_threads=4).num_threads == 4
+    assert set(["FTLE", "LCS", "AttractionRate", "RepulsionRate", "iLES", "TrajectoryRepulsionRate",
+                "TrajectoryRepulsionRatio"]) <= set(dir(D))
+    if not torch.cuda.is_available():  # the product fails loudly without a device
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            D.FTLE().compute([0, 1, 2], [0, 1], __import__("dynlab_b200").flows.double_gyre, (2, 0))
+
+
+def test_marching_squares_simple():
+    from dynlab_b200._contour import marching_squares
+
+    x = np.linspace(-1, 1, 21)
+    y = np.linspace(-1, 1, 17)
+    X, Y = np.meshgrid(x, y)
+    lines = marching_squares(x, y, X - 0.33 * Y + 0.05)
+    assert len(lines) == 1
+    L = lines[0]
+    assert np.abs(L[:, 0] - 0.33 * L[:, 1] + 0.05).max() < 1e-12
+    z = np.ma.MaskedArray(X ** 2 + Y ** 2 - 0.5, mask=(X > 0.5))
+    lines = marching_squares(x, y, z)
+    assert len(lines) == 1 and lines[0][:, 0].max() <= 0.5 + 1e-12
+    r = np.hypot(lines[0][:, 0], lines[0][:, 1])
+    assert np.abs(r - np.sqrt(0.5)).max() < 5e-3
+
+
+# ------------------------------------------------------------------ sharding (gloo)
+def test_partition_covers_grid():
+    from dynlab_b200.sharding import active_ranks, partition
+
+    for ydim in (2, 3, 5, 16, 101, 4096):
+        for size in (1, 2, 3, 8):
+            slabs = [partition(ydim, size, r) for r in range(size)]
+            n = active_ranks(ydim, size)
+            assert sum(s.rows for s in slabs) == ydim
+            rows = 0
+            for r, s in enumerate(slabs):
+                if r < n:
+                    assert s.row0 == rows and s.rows >= min(2, ydim)
+                    assert s.lo == max(s.row0 - 1, 0) and s.hi == min(s.row0 + s.rows + 1, ydim)
+                    rows += s.rows
+                else:
+                    assert s.rows == 0
+            assert max(s.rows for s in slabs) == slabs[0].rows_max
+
+
+def _shard_worker(rank, size, port, ydim, xdim, edge_order, out_dir):
+    """Each rank owns a row slab of a flow map, exchanges halos, runs the ORACLE stencil on its
+    local rows (test infrastructure standing in for K2) and gathers; rank 0 checks the result
+    against the unsharded oracle."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        from dynlab_b200 import sharding
+        from oracle import py_oracle as po
+
+        rng = np.random.default_rng(3)
+        x = np.sort(rng.uniform(0, 2, xdim))
+        y = np.linspace(0, 1, ydim)
+        fm = rng.normal(size=(ydim, xdim, 2))
+        full = np.ma.getdata(po.ftle_from_flow_map(fm, x, y, (0, 2), edge_order))
+
+        assert sharding.world() == (rank, size)
+        slab = sharding.partition(ydim, size, rank)
+        local = torch.zeros(max(slab.nloc, 1), xdim, 2, dtype=torch.float64)
+        if slab.rows:  # "K1": own rows only
+            local[slab.halo_lo:slab.halo_lo + slab.rows] = torch.from_numpy(fm[slab.row0:slab.row0 + slab.rows])
+        sharding.exchange_halo(local, slab, ydim, rank, size)
+        if slab.rows:
+            assert np.array_equal(local[:slab.nloc].numpy(), fm[slab.lo:slab.hi])
+        out = torch.zeros(slab.rows_max, xdim, dtype=torch.float64)
+        if slab.rows:
+            # local stencil: one-sided formulas only at global edges -> evaluate the oracle on
+            # the local rows and keep the rows whose stencil lay inside
+            loc = np.ma.getdata(po.ftle_from_flow_map(local[:slab.nloc].numpy(), x, y[slab.lo:slab.hi], (0, 2), edge_order))
+            out[:slab.rows] = torch.from_numpy(loc[slab.halo_lo:slab.halo_lo + slab.rows])
+        got = sharding.gather_rows(out, ydim, size).numpy()
+        assert got.shape == full.shape
+        # rows next to an interior cut used a one-sided oracle formula locally only if the slab
+        # had no halo there — with halos every own row matches the unsharded result
+        np.testing.assert_allclose(got, full, rtol=1e-12, atol=1e-12)
+        sharding.set_distributed(False)
+        assert sharding.world() == (0, 1)
+        sharding.set_distributed(True)
+        if rank == 0:
+            open(os.path.join(out_dir, f"ok_{size}_{ydim}_{edge_order}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("size,ydim,edge_order", [(2, 16, 2), (2, 7, 1), (3, 11, 2), (2, 3, 2)])
+def test_sharded_halo_and_gather_gloo(tmp_path, size, ydim, edge_order):
+    port = 29500 + (os.getpid() + size * 17 + ydim) % 2000
+    mp.spawn(_shard_worker, args=(size, port, ydim, 9, edge_order, str(tmp_path)), nprocs=size, join=True)
+    assert os.path.exists(tmp_path / f"ok_{size}_{ydim}_{edge_order}")
