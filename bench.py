@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — FTLE seeds/s on BASELINE config 3 (double gyre 8192x4096, t=(10,0), T=10,
+edge_order=2, rtol=atol=1e-8), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the hot path over the whole seed grid:
+K1 (RK45 flow map of this rank's row slab) -> 1-row halo exchange -> K2 (fused stencil/eigen)
+-> gather of the FTLE rows.
+  value : seeds/s with everything resident in HBM (CUDA events, max over ranks).
+  e2e   : seeds/s through the public API FTLE().compute(x, y, f, t, ...) with host numpy
+          coordinates in and the host FTLE field out (pinned D2H inside the timed region).
+  roofline      : K1, FP64-bound: algorithmic FLOP (SURVEY §8d model, from the kernel's exact
+                  attempt counter) / K1's mean launch duration, against the DFMA peak measured
+                  in this run (MEASURED_PEAKS.json has no FP64 figure).
+  roofline_hbm  : K2, HBM-bound: 24 B/point / launch duration against MEASURED_PEAKS hbm_gbs.
+  cpu_baseline  : the plain-C oracle port of the same algorithm on all host cores, bounded
+                  strided sample of the same grid (rank 0, N=1 only).
+--impl reference times the reference's own CPU implementation of the path (faithful Python
+port: scipy LSODA through the seed loop with a process pool over all cores + np.gradient +
+np.linalg.eig loop, oracle/py_oracle.py) on a bounded strided sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "FTLE seeds/sec at 8192x4096 double gyre T=10"
+XDIM, YDIM = 8192, 4096
+T_SPAN = (10, 0)
+TOL = 1e-8
+EDGE_ORDER = 2
+
+# SURVEY §8d FLOP model (FMA = 2, W = 20 flop per transcendental call), double gyre, n = 2
+F_RHS = 18 + 5 * 20
+F_ATTEMPT = 6 * F_RHS + 64 * 2 + 16 + 20   # 872
+F_SEED = 2 * F_RHS + 10 * 2                # 256
+BYTES_PER_POINT_K2 = 24
+
+
+def grid(stride: int = 1):
+    x = np.linspace(0, 2, XDIM)[::stride]
+    y = np.linspace(0, 1, YDIM)[::stride]
+    return np.ascontiguousarray(x), np.ascontiguousarray(y)
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6),
+                              ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if r[col].lower().startswith("active"):
+                    reasons.add(name)
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------- CPU legs
+def cpu_baseline_c_port(target_s: float = 12.0):
+    """oracle/c (plain-C restatement of scipy RK45 + np.gradient + closed-form eigen), all host
+    cores, on a strided sub-grid of config 3 sized for ~target_s seconds."""
+    from oracle import c_oracle as co
+    from oracle import py_oracle as po
+
+    cores = host_cores()
+    p = po.flow_params("double_gyre")
+    x, y = grid(64)
+    t0 = time.perf_counter()
+    co.flow_map("double_gyre", p, x, y, 10.0, 0.0, TOL, TOL, nthreads=cores)
+    rate = x.size * y.size / (time.perf_counter() - t0)
+    stride = 64
+    while stride > 2 and (XDIM // (stride // 2)) * (YDIM // (stride // 2)) / rate < target_s:
+        stride //= 2
+    x, y = grid(stride)
+    t0 = time.perf_counter()
+    fm, nfev, st = co.flow_map("double_gyre", p, x, y, 10.0, 0.0, TOL, TOL, nthreads=cores)
+    co.ftle(fm, y, x, 10.0, 0.0, EDGE_ORDER)
+    dt = time.perf_counter() - t0
+    n = x.size * y.size
+    return {"value": n / dt, "unit": "seeds/s", "cores": cores, "kind": "port",
+            "sample": f"every {stride}th row and column of the 8192x4096 grid "
+                      f"({x.size}x{y.size} = {n} seeds, {dt:.1f} s), oracle/c RK45 port, "
+                      f"{cores} threads", "mean_nfev": float(nfev.mean())}
+
+
+def reference_python_port(seeds_target: int, integrator: str = "lsoda"):
+    """The reference's own algorithm, restated in oracle/py_oracle.py: per-seed scipy solve
+    through a process pool over all cores (R:_base_classes.py:139-148,178-185), then
+    np.gradient and the per-point eig loop (R:lagrangian.py:50-76)."""
+    from oracle import py_oracle as po
+
+    cores = host_cores()
+    stride = 64
+    while stride > 1 and (XDIM // stride) * (YDIM // stride) < seeds_target:
+        stride //= 2
+    x, y = grid(stride)
+    integ = po.odeint_wrapper if integrator == "lsoda" else po.rk45_wrapper
+    f = po.FlowSpec("double_gyre")
+    t0 = time.perf_counter()
+    fm = po.flow_map(x, y, f, T_SPAN, integrator=integ, num_threads=cores, rtol=TOL, atol=TOL)
+    po.ftle_from_flow_map(fm, x, y, T_SPAN, EDGE_ORDER)
+    dt = time.perf_counter() - t0
+    n = x.size * y.size
+    return n / dt, dt, f"every {stride}th row and column of the 8192x4096 grid ({x.size}x{y.size} = {n} seeds)", cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    times, sample, n_seeds = [], "", 0
+    target = max(2048, 600 * cores)
+    for i in range(args.warmup + args.steps):
+        v, dt, sample, cores = reference_python_port(target)
+        if i >= args.warmup:
+            times.append(dt)
+            n_seeds = v * dt
+    ms = 1e3 * float(np.mean(times))
+    value = n_seeds / (ms * 1e-3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "seeds/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "FTLE double_gyre 8192x4096, t=(10,0), edge_order=2, "
+                               "rtol=atol=1e-8 (BASELINE configs[2]); each step = " + sample},
+        "cpu_baseline": {"value": value, "unit": "seeds/s", "cores": cores, "kind": "port",
+                         "sample": sample + "; oracle/py_oracle.py: scipy odeint (LSODA, the "
+                                   "reference's default integrator) per seed through a process "
+                                   "pool over all cores + np.gradient + np.linalg.eig"},
+        "e2e": {"value": value, "unit": "seeds/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: dynlab_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from dynlab_b200 import sharding
+    from dynlab_b200._engine import Engine
+    from dynlab_b200.diagnostics import FTLE
+    from dynlab_b200.flows import double_gyre
+
+    eng = Engine.get()
+    x, y = grid(1)
+    n_seeds = XDIM * YDIM
+    diag = FTLE()
+    kw = dict(edge_order=EDGE_ORDER, rtol=TOL, atol=TOL)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # FP64 peak of this GPU, measured in this run (roofline denominator for K1)
+    peak_flops, _ = eng.dfma_peak(2048)
+    peak_flops, _ = eng.dfma_peak(8192)
+
+    # ---------------- device-resident loop: `value` ----------------
+    for _ in range(args.warmup):
+        diag.compute_device(x, y, double_gyre, T_SPAN, **kw)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.profile = {}
+    launches0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        diag.compute_device(x, y, double_gyre, T_SPAN, **kw)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = eng.launches - launches0
+    prof, eng.profile = eng.profile, None
+    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in prof["rk45_flowmap"]]))
+    k2_ms = float(np.mean([a.elapsed_time(b) for a, b in prof["ftle_stencil"]]))
+    stats = eng.read_counters()  # last K1 launch on this rank
+    slab = sharding.partition(YDIM, world, rank)
+    ms_step = ms_total / args.steps
+    value = n_seeds / (ms_step * 1e-3)
+
+    # ---------------- end-to-end through the public API: `e2e` ----------------
+    for _ in range(max(1, min(args.warmup, 2))):
+        diag.compute(x, y, double_gyre, T_SPAN, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        field = diag.compute(x, y, double_gyre, T_SPAN, **kw)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    h2d = (XDIM + slab.rows) * 8 + 3 * 8 * (XDIM + YDIM)      # coordinates + stencil coefficients
+    d2h = field.size * 8 + 64                                  # FTLE field + counters
+
+    if rank == 0:
+        attempts = (stats["nfev"] - 2 * stats["seeds"]) / 6.0
+        k1_flop = attempts * F_ATTEMPT + stats["seeds"] * F_SEED
+        achieved = k1_flop / (k1_ms * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        k2_gbs = BYTES_PER_POINT_K2 * slab.rows * XDIM / (k2_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "seeds/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "FTLE double_gyre 8192x4096, t=(10,0), edge_order=2, "
+                                   "rtol=atol=1e-8 (BASELINE configs[2])",
+                       "parallelism": f"row slabs over {world} GPU(s); 1-row halo exchange + "
+                                      "all-gather" if world > 1 else "single GPU",
+                       "l2": "inputs/outputs (537 MB flow map + 268 MB field per step) exceed "
+                             "the 126 MB L2; no flush needed",
+                       "integrator": {"mean_nfev_per_seed": stats["nfev"] / max(stats["seeds"], 1),
+                                      "rejected_attempts": stats["rejected"],
+                                      "failed_seeds": stats["failed"]}},
+            "e2e": {"value": n_seeds / e2e_s, "unit": "seeds/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": launches,
+            "kernels_ms": {"rk45_flowmap": k1_ms, "ftle_stencil": k2_ms},
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak_flops / 1e12,
+                         "unit": "TFLOP/s", "frac": achieved / peak_flops, "traffic": None,
+                         "kernel": "rk45_kernel<double_gyre> (K1)",
+                         "note": "algorithmic FLOP = attempts*872 + seeds*256 (SURVEY §8d model, "
+                                 "attempts counted by the kernel); peak = DFMA chain measured "
+                                 "in this run (dlb_dfma_peak), theoretical 37.2 TFLOP/s at "
+                                 "1965 MHz"},
+            "roofline_hbm": {"bound": "hbm", "achieved": k2_gbs, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": k2_gbs / hbm_peak, "traffic": None,
+                             "kernel": "stencil_kernel<FTLE> (K2)",
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_c_port()
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

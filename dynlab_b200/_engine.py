@@ -49,6 +49,28 @@ class Engine:
         self.device = torch.device("cuda", index)
         self._workspace = None
         self.counters = torch.zeros(nat.CNT_WORDS, dtype=torch.int64, device=self.device)
+        self.profile = None  # set to {} to collect (start, end) CUDA events per kernel name
+        self.launches = 0    # kernels of libdynlab_b200.so launched through this engine
+
+    def _timed(self, name, n_kernels=1):
+        """Context manager: count launches; record CUDA events around them when profiling."""
+        eng = self
+
+        class _T:
+            def __enter__(self_t):
+                if eng.profile is not None:
+                    self_t.e0 = torch.cuda.Event(enable_timing=True)
+                    self_t.e1 = torch.cuda.Event(enable_timing=True)
+                    self_t.e0.record(torch.cuda.current_stream(eng.device))
+
+            def __exit__(self_t, *exc):
+                eng.launches += n_kernels
+                if eng.profile is not None:
+                    self_t.e1.record(torch.cuda.current_stream(eng.device))
+                    eng.profile.setdefault(name, []).append((self_t.e0, self_t.e1))
+                return False
+
+        return _T()
 
     # -- plumbing ---------------------------------------------------------------------
     def stream(self) -> int:
@@ -91,7 +113,8 @@ class Engine:
                 out = self.empty(rows, xdim, 2)
             ws, wsz = self.workspace(xdim, max(len(y), rows))
             p = nat.darray(params)
-            nat.check(nat.lib.dlb_flowmap_rk45(
+            with self._timed("rk45_flowmap"):
+              nat.check(nat.lib.dlb_flowmap_rk45(
                 flow_id, p, len(params), nat.dptr(x), xdim, nat.dptr(y), row0, rows,
                 float(t0), float(tf), float(rtol), float(atol), float(max_step), float(first_step),
                 out.data_ptr(), nfev.data_ptr() if nfev is not None else None,
@@ -107,7 +130,8 @@ class Engine:
             ws, wsz = self.workspace(0, 0)
             p = nat.darray(params)
             a = nat.darray(np.broadcast_to(np.asarray(atol, dtype=np.float64), (n,)))
-            nat.check(nat.lib.dlb_rk45_endpoints(
+            with self._timed("rk45_endpoints"):
+              nat.check(nat.lib.dlb_rk45_endpoints(
                 flow_id, p, len(params), n, seeds.data_ptr(), m, float(t0), float(tf),
                 float(rtol), a, float(max_step), float(first_step), out.data_ptr(),
                 nfev.data_ptr() if nfev is not None else None,
@@ -125,7 +149,8 @@ class Engine:
                 out = self.empty(out_rows, xdim)
             xi = self.empty(out_rows, xdim, 2) if xi_mode != nat.XI_NONE else None
             ws, wsz = self.workspace(xdim, ydim)
-            nat.check(nat.lib.dlb_ftle_stencil(
+            with self._timed("ftle_stencil"):
+              nat.check(nat.lib.dlb_ftle_stencil(
                 fm_local.data_ptr(), nloc, grow0, nat.dptr(x), xdim, nat.dptr(y), ydim,
                 int(edge_order), float(t_span), out_row0, out_rows, out.data_ptr(),
                 xi.data_ptr() if xi is not None else None, xi_mode, ws, wsz, self.stream()))
@@ -142,7 +167,8 @@ class Engine:
             mask = self.empty(out_rows, xdim, dtype=torch.uint8) if need_mask else None
             xi = self.empty(out_rows, xdim, 2) if xi_mode != nat.XI_NONE else None
             ws, wsz = self.workspace(xdim, ydim)
-            nat.check(nat.lib.dlb_euler_stencil(
+            with self._timed("euler_stencil"):
+              nat.check(nat.lib.dlb_euler_stencil(
                 mode, u_local.data_ptr(), v_local.data_ptr(), nloc, grow0, nat.dptr(x), xdim,
                 nat.dptr(y), ydim, int(edge_order), out_row0, out_rows, int(bool(negate)),
                 out.data_ptr(), mask.data_ptr() if mask is not None else None,
@@ -156,7 +182,8 @@ class Engine:
             u, v = self.empty(ydim, xdim), self.empty(ydim, xdim)
             ws, wsz = self.workspace(xdim, ydim)
             p = nat.darray(params)
-            nat.check(nat.lib.dlb_flow_eval_grid(
+            with self._timed("flow_eval"):
+              nat.check(nat.lib.dlb_flow_eval_grid(
                 flow_id, p, len(params), float(t), nat.dptr(x), xdim, nat.dptr(y), ydim,
                 u.data_ptr(), v.data_ptr(), ws, wsz, self.stream()))
         return u, v
@@ -167,7 +194,8 @@ class Engine:
         with torch.cuda.device(self.device):
             out = self.empty(dim, n)
             p = nat.darray(params)
-            nat.check(nat.lib.dlb_flow_eval_points(
+            with self._timed("flow_eval"):
+              nat.check(nat.lib.dlb_flow_eval_points(
                 flow_id, p, len(params), float(t), pts[0].data_ptr(), pts[1].data_ptr(),
                 pts[2].data_ptr() if dim == 3 else None, n, out[0].data_ptr(), out[1].data_ptr(),
                 out[2].data_ptr() if dim == 3 else None, self.stream()))
@@ -181,7 +209,8 @@ class Engine:
             mask = self.empty(ydim, xdim, dtype=torch.uint8)
             scratch = self.empty(ydim, xdim, 2)
             ws, wsz = self.workspace(xdim, ydim)
-            nat.check(nat.lib.dlb_ridge_field(
+            with self._timed("ridge_field", 2):
+              nat.check(nat.lib.dlb_ridge_field(
                 field.data_ptr(), xi.data_ptr(), nat.dptr(x), xdim, nat.dptr(y), ydim,
                 int(edge_order), int(threshold is not None),
                 float(threshold if threshold is not None else 0.0), dd.data_ptr(),

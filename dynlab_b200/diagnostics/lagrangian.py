@@ -50,12 +50,18 @@ class FTLE(LagrangianDiagnostic2D):
         """Returns ``np.ma.MaskedArray[ydim, xdim]``; sets ``x, y, xdim, ydim, flow_map,
         field`` like the reference.  ``kwargs`` (rtol, atol, max_step, first_step) go to the
         integrator."""
-        local, slab = super().compute(x, y, f, t, **kwargs)
-        field, _ = _ftle_on_device(self, local, slab, t, edge_order, nat.XI_NONE)
-        self.field_device = field
+        field = self.compute_device(x, y, f, t, edge_order, **kwargs)
         self.field = np.ma.MaskedArray(Engine.get().to_host(field))
         self._collect_stats()
         return self.field
+
+    def compute_device(self, x, y, f, t, edge_order: int = 1, **kwargs):
+        """Same computation, result left on the device (``torch.Tensor[ydim, xdim]``, also kept
+        as ``field_device``); nothing is synchronised or copied to the host."""
+        local, slab = super().compute(x, y, f, t, **kwargs)
+        field, _ = _ftle_on_device(self, local, slab, t, edge_order, nat.XI_NONE)
+        self.field_device = field
+        return field
 
 
 class LCS(LagrangianDiagnostic2D, RidgeExtractor2D):
