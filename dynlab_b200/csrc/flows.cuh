@@ -86,21 +86,124 @@ static inline bool flow_prepare(int id, const double* p, int n_params, FlowConst
   return true;
 }
 
-// f(t, Y) for flow ID.  Y/out have k_flow_info[ID].dim entries.
+// ---- time / space split --------------------------------------------------------------------
+// f(t, Y) = flow_space(flow_time(t), Y).  Within one Runge-Kutta attempt the six stage times
+// are known up front (t + c_s h), so the integrator evaluates the time parts of all stages in
+// one interleaved block (independent polynomial chains, constants loaded once) and reuses the
+// value at t + h for the two stages that share it (c_6 = c_7 = 1).  tc[] holds FlowTime<ID>::N
+// doubles: the separable forcing term where there is one, otherwise t itself.
 template <int ID>
-__device__ __forceinline__ void flow_rhs(const FlowConsts& fc, double t, const double* Y,
-                                         double* out) {
+struct FlowTime {
+  static constexpr int N = 1;  // default: tc[0] = t
+};
+#define DLB_AUTONOMOUS(id)          \
+  template <>                       \
+  struct FlowTime<id> {             \
+    static constexpr int N = 0;     \
+  };
+DLB_AUTONOMOUS(DLB_FLOW_AUTONOMOUS_DOUBLE_GYRE)
+DLB_AUTONOMOUS(DLB_FLOW_GLIDER)
+DLB_AUTONOMOUS(DLB_FLOW_HILLS_VORTEX)
+DLB_AUTONOMOUS(DLB_FLOW_AUTONOMOUS_DUFFING)
+DLB_AUTONOMOUS(DLB_FLOW_BEAD)
+DLB_AUTONOMOUS(DLB_FLOW_LOTKA_VOLTERRA)
+DLB_AUTONOMOUS(DLB_FLOW_LORENZ)
+#undef DLB_AUTONOMOUS
+
+// Time part for NS stage times at once (NS = 1 or 5).  tc is [NS][max(N, 1)].
+template <int ID, int NS>
+__device__ __forceinline__ void flow_time(const FlowConsts& fc, const double* t,
+                                          double (*tc)[FlowTime<ID>::N > 0 ? FlowTime<ID>::N : 1]) {
+  const double* c = fc.c;
+  if constexpr (ID == DLB_FLOW_DOUBLE_GYRE || ID == DLB_FLOW_DUFFING || ID == DLB_FLOW_PENDULUM ||
+                ID == DLB_FLOW_VAN_DER_POL || ID == DLB_FLOW_HURRICANE || ID == DLB_FLOW_ABC) {
+    // one sin (cos for hurricane) of (frequency * t) per stage
+    constexpr bool is_cos = (ID == DLB_FLOW_HURRICANE);
+    const double w = (ID == DLB_FLOW_DOUBLE_GYRE) ? c[0]
+                     : (ID == DLB_FLOW_DUFFING || ID == DLB_FLOW_PENDULUM) ? c[2]
+                     : (ID == DLB_FLOW_VAN_DER_POL) ? c[3]
+                     : (ID == DLB_FLOW_HURRICANE) ? c[1]
+                                                  : DLB_PI;
+    double arg[NS];
+    int big = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      arg[s] = w * t[s];
+      big = max(big, dm::hi_abs(arg[s]));
+    }
+    if (big >= DM_TRIG_BIG_HI) {  // huge / inf / nan: CUDA's Payne-Hanek path
+#pragma unroll
+      for (int s = 0; s < NS; ++s) tc[s][0] = is_cos ? ::cos(arg[s]) : ::sin(arg[s]);
+    } else {
+      double r[NS], z[NS], ps[NS], pc[NS];
+      int q[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) r[s] = dm::reduce_pio2(arg[s], &q[s]);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        z[s] = r[s] * r[s];
+        ps[s] = fma(DM_S(6), z[s], DM_S(5));
+        pc[s] = fma(DM_C(6), z[s], DM_C(5));
+      }
+#pragma unroll
+      for (int k = 4; k >= 1; --k) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          ps[s] = fma(ps[s], z[s], DM_S(k));
+          pc[s] = fma(pc[s], z[s], DM_C(k));
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const double sn = fma(r[s] * z[s], ps[s], r[s]);
+        const double cs = fma(z[s] * z[s], pc[s], fma(-0.5, z[s], 1.0));
+        tc[s][0] = is_cos ? dm::fix_cos(sn, cs, q[s]) : dm::fix_sin(sn, cs, q[s]);
+      }
+    }
+  } else if constexpr (FlowTime<ID>::N == 1) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) tc[s][0] = t[s];
+  }
+}
+
+// Space part.  Y/out have k_flow_info[ID].dim entries.
+template <int ID>
+__device__ __forceinline__ void flow_space(const FlowConsts& fc, const double* tc, const double* Y,
+                                           double* out) {
   const double* c = fc.c;
   const double x = Y[0], y = Y[1];
   if constexpr (ID == DLB_FLOW_DOUBLE_GYRE) {
-    const double s = dm::sin(c[0] * t);
+    const double s = tc[0];  // sin(w t)
     const double a = c[1] * s;
     const double b = 1 - c[2] * s;
     const double f = a * (x * x) + b * x;
     const double dfdx = 2 * a * x + b;
+    const double af = DLB_PI * f, ay = y * DLB_PI;
     double sf, cf, sy, cy;
-    dm::sincos(DLB_PI * f, &sf, &cf);
-    dm::sincos(y * DLB_PI, &sy, &cy);
+    if (max(dm::hi_abs(af), dm::hi_abs(ay)) >= DM_TRIG_BIG_HI) {
+      ::sincos(af, &sf, &cf);
+      ::sincos(ay, &sy, &cy);
+    } else {  // two interleaved sincos
+      int qf, qy;
+      const double rf = dm::reduce_pio2(af, &qf), ry = dm::reduce_pio2(ay, &qy);
+      const double zf = rf * rf, zy = ry * ry;
+      double psf = fma(DM_S(6), zf, DM_S(5)), psy = fma(DM_S(6), zy, DM_S(5));
+      double pcf = fma(DM_C(6), zf, DM_C(5)), pcy = fma(DM_C(6), zy, DM_C(5));
+#pragma unroll
+      for (int k = 4; k >= 1; --k) {
+        psf = fma(psf, zf, DM_S(k));
+        psy = fma(psy, zy, DM_S(k));
+        pcf = fma(pcf, zf, DM_C(k));
+        pcy = fma(pcy, zy, DM_C(k));
+      }
+      const double snf = fma(rf * zf, psf, rf), sny = fma(ry * zy, psy, ry);
+      const double csf = fma(zf * zf, pcf, fma(-0.5, zf, 1.0));
+      const double csy = fma(zy * zy, pcy, fma(-0.5, zy, 1.0));
+      sf = dm::fix_sin(snf, csf, qf);
+      cf = dm::fix_cos(snf, csf, qf);
+      sy = dm::fix_sin(sny, csy, qy);
+      cy = dm::fix_cos(sny, csy, qy);
+    }
     out[0] = c[3] * sf * cy;
     out[1] = c[4] * cf * sy * dfdx;
   } else if constexpr (ID == DLB_FLOW_AUTONOMOUS_DOUBLE_GYRE) {
@@ -110,6 +213,7 @@ __device__ __forceinline__ void flow_rhs(const FlowConsts& fc, double t, const d
     out[0] = -DLB_PI * sx * cy;
     out[1] = DLB_PI * cx * sy;
   } else if constexpr (ID == DLB_FLOW_BICKLEY_JET) {
+    const double t = tc[0];
     const double yl = y / c[1];
     const double ch = 1 / cosh(yl);
     const double sech2 = ch * ch, th = tanh(yl);
@@ -131,25 +235,25 @@ __device__ __forceinline__ void flow_rhs(const FlowConsts& fc, double t, const d
     out[0] = 2.0 * x * y;
     out[1] = -2.0 * (2.0 * x * x - 1.0) - 2.0 * y * y;
   } else if constexpr (ID == DLB_FLOW_SIGMOIDAL) {
-    out[0] = 0.4 * tanh(10.0 * (x - 0.5 * t));
+    out[0] = 0.4 * tanh(10.0 * (x - 0.5 * tc[0]));
     out[1] = y * 0;
   } else if constexpr (ID == DLB_FLOW_AUTONOMOUS_DUFFING) {
     out[0] = y;
     out[1] = x - x * x * x;
-  } else if constexpr (ID == DLB_FLOW_DUFFING) {  // A, gamma, omega
+  } else if constexpr (ID == DLB_FLOW_DUFFING) {  // A, gamma, omega; tc = sin(omega t)
     out[0] = y;
-    out[1] = x - x * x * x - c[1] * y + c[0] * dm::sin(c[2] * t);
-  } else if constexpr (ID == DLB_FLOW_PENDULUM) {  // A, gamma, omega
+    out[1] = x - x * x * x - c[1] * y + c[0] * tc[0];
+  } else if constexpr (ID == DLB_FLOW_PENDULUM) {  // A, gamma, omega; tc = sin(omega t)
     out[0] = y;
-    out[1] = -dm::sin(x) - c[1] * y + c[0] * dm::sin(c[2] * t);
-  } else if constexpr (ID == DLB_FLOW_HURRICANE) {
+    out[1] = -dm::sin(x) - c[1] * y + c[0] * tc[0];
+  } else if constexpr (ID == DLB_FLOW_HURRICANE) {  // tc = cos(eye_omega t)
     const double yt = y - c[4];
     const double den = x * x + yt * yt + c[0];
     out[0] = -yt / den - c[3];
-    out[1] = x / den + c[2] * y * dm::cos(c[1] * t);
-  } else if constexpr (ID == DLB_FLOW_VAN_DER_POL) {  // A, mu, gamma, omega
+    out[1] = x / den + c[2] * y * tc[0];
+  } else if constexpr (ID == DLB_FLOW_VAN_DER_POL) {  // A, mu, gamma, omega; tc = sin(omega t)
     out[0] = y;
-    out[1] = c[1] * (1 - x * x) * y - x - c[2] * y + c[0] * dm::sin(c[3] * t);
+    out[1] = c[1] * (1 - x * x) * y - x - c[2] * y + c[0] * tc[0];
   } else if constexpr (ID == DLB_FLOW_BEAD) {  // 1/epsilon, gamma
     double s, cs;
     dm::sincos(x, &s, &cs);
@@ -158,9 +262,9 @@ __device__ __forceinline__ void flow_rhs(const FlowConsts& fc, double t, const d
   } else if constexpr (ID == DLB_FLOW_LOTKA_VOLTERRA) {  // alpha, beta, gamma, delta
     out[0] = c[0] * x - c[1] * x * y;
     out[1] = c[3] * x * y - c[2] * y;
-  } else if constexpr (ID == DLB_FLOW_ABC) {  // ABC_Amplitude, A, B, C
+  } else if constexpr (ID == DLB_FLOW_ABC) {  // ABC_Amplitude, A, B, C; tc = sin(pi t)
     const double z = Y[2];
-    const double At = c[1] + c[0] * dm::sin(DLB_PI * t);
+    const double At = c[1] + c[0] * tc[0];
     double sx, cx, sy, cy, sz, cz;
     dm::sincos(x, &sx, &cx);
     dm::sincos(y, &sy, &cy);
@@ -174,6 +278,15 @@ __device__ __forceinline__ void flow_rhs(const FlowConsts& fc, double t, const d
     out[1] = x * (c[1] - z) - y;
     out[2] = x * y - c[2] * z;
   }
+}
+
+// f(t, Y) in one call (K0 and the integrator's start-up evaluations).
+template <int ID>
+__device__ __forceinline__ void flow_rhs(const FlowConsts& fc, double t, const double* Y,
+                                         double* out) {
+  double tc[1][FlowTime<ID>::N > 0 ? FlowTime<ID>::N : 1];
+  flow_time<ID, 1>(fc, &t, tc);
+  flow_space<ID>(fc, tc[0], Y, out);
 }
 
 // Run the statement block with `constexpr int ID` bound to the runtime flow id.

@@ -117,6 +117,18 @@ __device__ __forceinline__ double rms_norm(const double* v) {
   return sqrt(s) * (N == 2 ? 0.70710678118654752440 : 0.57735026918962576451);
 }
 
+// |nextafter(t, dir * inf) - t| (rk.py:119) from the bit pattern: the spacing of doubles
+// at t in the direction of integration.
+__device__ __forceinline__ double ulp_towards(double t, double dir) {
+  const long long b = __double_as_longlong(t);
+  const long long mag = b & 0x7fffffffffffffffLL;
+  if (mag >= 0x7ff0000000000000LL) return fabs(nextafter(t, dir * CUDART_INF) - t);  // inf / nan
+  if (mag == 0) return 4.9406564584124654e-324;  // nextafter(0, +-inf) = +-denorm_min
+  const bool away = ((b < 0) == (dir < 0));      // moving away from zero?
+  const double nb = __longlong_as_double(away ? b + 1 : b - 1);
+  return fabs(nb - t);
+}
+
 template <int ID, int N, bool GRID>
 __global__ void __launch_bounds__(RK_BLOCK) rk45_kernel(const Rk45Params P) {
   const unsigned lane = threadIdx.x & 31u;
@@ -234,7 +246,7 @@ __global__ void __launch_bounds__(RK_BLOCK) rk45_kernel(const Rk45Params P) {
 
     // ---------------- one RK45 attempt: rk.py:111-176 ----------------
     if (active) {
-      const double min_step = 10.0 * fabs(nextafter(t, dir * CUDART_INF) - t);  // rk.py:119
+      const double min_step = 10.0 * ulp_towards(t, dir);  // rk.py:119
       if (fresh) {  // start of _step_impl: clamp once per step (rk.py:121-126)
         if (h_abs > P.max_step)
           h_abs = P.max_step;
@@ -252,54 +264,67 @@ __global__ void __launch_bounds__(RK_BLOCK) rk45_kernel(const Rk45Params P) {
         h = t_new - t;
         h_abs = fabs(h);
 
+        // time parts of all stages in one block; stages 6 and 7 share t + h (C[5] = 1)
+        constexpr int NT = FlowTime<ID>::N > 0 ? FlowTime<ID>::N : 1;
+        double ts[5], tc[5][NT];
+        ts[0] = fma(C1, h, t);
+        ts[1] = fma(C2, h, t);
+        ts[2] = fma(C3, h, t);
+        ts[3] = fma(C4, h, t);
+        ts[4] = t + h;
+        flow_time<ID, 5>(P.fc, ts, tc);
+
         // rk_step, rk.py:60-69.  K0 = f (FSAL)
         double K1[N], K2[N], K3[N], K4[N], K5[N], K6[N], ys[N], yn[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) ys[i] = fma(f[i] * A10, h, y[i]);
-        flow_rhs<ID>(P.fc, t + C1 * h, ys, K1);
+        flow_space<ID>(P.fc, tc[0], ys, K1);
 #pragma unroll
         for (int i = 0; i < N; ++i) ys[i] = fma(fma(K1[i], A21, f[i] * A20), h, y[i]);
-        flow_rhs<ID>(P.fc, t + C2 * h, ys, K2);
+        flow_space<ID>(P.fc, tc[1], ys, K2);
 #pragma unroll
         for (int i = 0; i < N; ++i)
           ys[i] = fma(fma(K2[i], A32, fma(K1[i], A31, f[i] * A30)), h, y[i]);
-        flow_rhs<ID>(P.fc, t + C3 * h, ys, K3);
+        flow_space<ID>(P.fc, tc[2], ys, K3);
 #pragma unroll
         for (int i = 0; i < N; ++i)
           ys[i] = fma(fma(K3[i], A43, fma(K2[i], A42, fma(K1[i], A41, f[i] * A40))), h, y[i]);
-        flow_rhs<ID>(P.fc, t + C4 * h, ys, K4);
+        flow_space<ID>(P.fc, tc[3], ys, K4);
 #pragma unroll
         for (int i = 0; i < N; ++i)
           ys[i] = fma(
               fma(K4[i], A54, fma(K3[i], A53, fma(K2[i], A52, fma(K1[i], A51, f[i] * A50)))), h,
               y[i]);
-        flow_rhs<ID>(P.fc, t + h, ys, K5);  // C[5] = 1
+        flow_space<ID>(P.fc, tc[4], ys, K5);
 #pragma unroll
         for (int i = 0; i < N; ++i)
           yn[i] = fma(
               h, fma(K5[i], B5, fma(K4[i], B4, fma(K3[i], B3, fma(K2[i], B2, f[i] * B0)))), y[i]);
-        flow_rhs<ID>(P.fc, t + h, yn, K6);  // f_new
+        flow_space<ID>(P.fc, tc[4], yn, K6);  // f_new
         nfev_l += 6;
 
-        // error estimate and norm, rk.py:105-109,146-147
-        double e[N];
+        // error estimate, rk.py:105-109,146-147; s = error_norm^2 (no square root needed:
+        // error_norm < 1 <=> s < 1, error_norm ** -0.2 == s ** -0.1)
+        double ssum = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           const double sc = P.atol[i] + fmax(fabs(y[i]), fabs(yn[i])) * rtol;
           const double ee =
               fma(K6[i], E6,
                   fma(K5[i], E5, fma(K4[i], E4, fma(K3[i], E3, fma(K2[i], E2, f[i] * E0)))));
-          e[i] = ee * h / sc;
+          const double e = ee * h * dm::rcp(sc);
+          ssum = fma(e, e, ssum);
         }
-        const double err = rms_norm<N>(e);
+        const double s = ssum * (N == 2 ? 0.5 : (1.0 / 3.0));
 
-        // step-size controller, rk.py:149-165.  The power is taken on err clamped to
-        // [1e-6, 1e4]: outside it MAX_FACTOR / MIN_FACTOR win, so the result is unchanged.
-        double ec = (err < 1e4) ? err : 1e4;  // also maps NaN -> MIN_FACTOR like Python's max()
-        ec = fmax(ec, 1e-6);
-        const double pw = 0.9 * dm::pow_m02(ec);
-        if (err < 1.0) {
-          double factor = (err == 0.0) ? 10.0 : fmin(10.0, pw);
+        // step-size controller, rk.py:149-165.  The power is taken on s clamped to
+        // [1e-12, 1e8] (error_norm in [1e-6, 1e4]): outside it MAX_FACTOR / MIN_FACTOR win, so
+        // the result is unchanged; a NaN norm maps to MIN_FACTOR like Python's max().
+        double sc2 = (s < 1e8) ? s : 1e8;
+        sc2 = fmax(sc2, 1e-12);
+        const double pw = 0.9 * dm::pow_m01(sc2);
+        if (s < 1.0) {
+          double factor = (s == 0.0) ? 10.0 : fmin(10.0, pw);
           if (rejected) factor = fmin(1.0, factor);
           h_abs *= factor;
           t = t_new;
@@ -386,8 +411,8 @@ int fill_common(Rk45Params& P, int flow_id, const double* h_params, int n_params
   P.max_step = max_step;
   P.first_step = first_step;
   P.direction = (tf != t0) ? ((tf > t0) ? 1.0 : -1.0) : 1.0;  // base.py:164
-  P.chunk = env_int("DLB_RK45_CHUNK", 128);
-  P.refill_threshold = env_int("DLB_RK45_REFILL", 8);
+  P.chunk = env_int("DLB_RK45_CHUNK", 32);
+  P.refill_threshold = env_int("DLB_RK45_REFILL", 32);
   if (P.chunk < 32) P.chunk = 32;
   if (P.refill_threshold < 1) P.refill_threshold = 1;
   if (P.refill_threshold > 32) P.refill_threshold = 32;
