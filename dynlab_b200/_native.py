@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libdynlab_b200.so")
+LIB_PATH = os.environ.get("DLB_LIB_PATH") or os.path.join(_HERE, "_lib", "libdynlab_b200.so")
 
 DLB_OK, DLB_ERR_ARG, DLB_ERR_CUDA, DLB_ERR_TOO_SMALL, DLB_ERR_WORKSPACE = 0, -1, -2, -3, -4
 EULER_S_MIN, EULER_S_MAX, EULER_RATE, EULER_RATIO = 0, 1, 2, 3

@@ -53,13 +53,19 @@ __constant__ double DM_K[18] = {
     4.16666666666666019037e-02,    // C1
     0.0,
 };
-#define DM_2_OVER_PI dm::DM_K[0]
-#define DM_PIO2_1 dm::DM_K[1]
-#define DM_PIO2_2 dm::DM_K[2]
-#define DM_PIO2_3 dm::DM_K[3]
-#define DM_MAGIC dm::DM_K[4]
-#define DM_S(i) dm::DM_K[11 - (i)]  // S1..S6
-#define DM_C(i) dm::DM_K[17 - (i)]  // C1..C6
+// Constant provider: reads the table through the constant cache (LDCU into uniform registers).
+// (A register-resident copy was measured: the extra ~34 registers cost more in occupancy than
+// the ~100 LDCU per RK attempt it saves — 83 ms vs 76 ms on BASELINE config 3.)
+struct KC {
+  __device__ __forceinline__ double operator[](int i) const { return DM_K[i]; }
+};
+#define DM_2_OVER_PI K[0]
+#define DM_PIO2_1 K[1]
+#define DM_PIO2_2 K[2]
+#define DM_PIO2_3 K[3]
+#define DM_MAGIC K[4]
+#define DM_S(i) K[11 - (i)]  // S1..S6
+#define DM_C(i) K[17 - (i)]  // C1..C6
 
 // high word of 105615.0 (0x40F9C8F000000000): |x| < 105615 <=> (hi & 0x7fffffff) < this
 #define DM_TRIG_BIG_HI 0x40F9C8F0
@@ -72,7 +78,8 @@ __device__ __forceinline__ double xor_sign(double v, int signbit) {
 }
 
 // x -> r in [-pi/4, pi/4] and quadrant q (only q mod 4 matters); valid for |x| < 105615.
-__device__ __forceinline__ double reduce_pio2(double x, int* q) {
+template <class KT>
+__device__ __forceinline__ double reduce_pio2(const KT& K, double x, int* q) {
   const double t = fma(x, DM_2_OVER_PI, DM_MAGIC);
   *q = __double2loint(t);
   const double fq = t - DM_MAGIC;
@@ -82,7 +89,8 @@ __device__ __forceinline__ double reduce_pio2(double x, int* q) {
   return r;
 }
 
-__device__ __forceinline__ double k_sin(double r, double r2) {
+template <class KT>
+__device__ __forceinline__ double k_sin(const KT& K, double r, double r2) {
   double p = fma(DM_S(6), r2, DM_S(5));
   p = fma(p, r2, DM_S(4));
   p = fma(p, r2, DM_S(3));
@@ -91,13 +99,14 @@ __device__ __forceinline__ double k_sin(double r, double r2) {
   return fma(r * r2, p, r);
 }
 
-__device__ __forceinline__ double k_cos(double r2) {
+template <class KT>
+__device__ __forceinline__ double k_cos(const KT& K, double r2) {
   double p = fma(DM_C(6), r2, DM_C(5));
   p = fma(p, r2, DM_C(4));
   p = fma(p, r2, DM_C(3));
   p = fma(p, r2, DM_C(2));
   p = fma(p, r2, DM_C(1));
-  return fma(r2 * r2, p, fma(-0.5, r2, 1.0));  // 1 - r2/2 + r2^2 p
+  return fma(r2, fma(r2, p, -0.5), 1.0);  // 1 + r2 (-1/2 + r2 p)
 }
 
 // quadrant fix-up: (sin r, cos r, q) -> sin x, cos x
@@ -110,36 +119,147 @@ __device__ __forceinline__ double fix_cos(double sn, double cs, int q) {
 
 // Fast paths (|x| < 105615 assumed — caller checks trig_is_big).
 __device__ __forceinline__ void sincos_fast(double x, double* s, double* c) {
+  const KC K;
   int q;
-  const double r = reduce_pio2(x, &q);
+  const double r = reduce_pio2(K, x, &q);
   const double r2 = r * r;
-  const double sn = k_sin(r, r2), cs = k_cos(r2);
+  const double sn = k_sin(K, r, r2), cs = k_cos(K, r2);
   *s = fix_sin(sn, cs, q);
   *c = fix_cos(sn, cs, q);
 }
 __device__ __forceinline__ double sin_fast(double x) {
+  const KC K;
   int q;
-  const double r = reduce_pio2(x, &q);
+  const double r = reduce_pio2(K, x, &q);
   const double r2 = r * r;
-  return fix_sin(k_sin(r, r2), k_cos(r2), q);
+  return fix_sin(k_sin(K, r, r2), k_cos(K, r2), q);
 }
 __device__ __forceinline__ double cos_fast(double x) {
+  const KC K;
   int q;
-  const double r = reduce_pio2(x, &q);
+  const double r = reduce_pio2(K, x, &q);
   const double r2 = r * r;
-  return fix_cos(k_sin(r, r2), k_cos(r2), q);
+  return fix_cos(k_sin(K, r, r2), k_cos(K, r2), q);
 }
 
-// General entry points: one well-predicted branch to the library for huge / inf / nan.
+// Out-of-line library paths for huge / inf / nan arguments (CUDA's Payne-Hanek reduction);
+// kept out of the hot loops so that they cost neither registers nor instruction cache.
+static __device__ __noinline__ double2 sincos_slow(double x) {
+  double s, c;
+  ::sincos(x, &s, &c);
+  return make_double2(s, c);
+}
+static __device__ __noinline__ double sin_slow(double x) { return ::sin(x); }
+static __device__ __noinline__ double cos_slow(double x) { return ::cos(x); }
+
+// General entry points: one well-predicted branch for huge / inf / nan.
 __device__ __forceinline__ void sincos(double x, double* s, double* c) {
   if (trig_is_big(x)) {
-    ::sincos(x, s, c);
+    const double2 sc = sincos_slow(x);
+    *s = sc.x;
+    *c = sc.y;
     return;
   }
   sincos_fast(x, s, c);
 }
-__device__ __forceinline__ double sin(double x) { return trig_is_big(x) ? ::sin(x) : sin_fast(x); }
-__device__ __forceinline__ double cos(double x) { return trig_is_big(x) ? ::cos(x) : cos_fast(x); }
+__device__ __forceinline__ double sin(double x) { return trig_is_big(x) ? sin_slow(x) : sin_fast(x); }
+__device__ __forceinline__ double cos(double x) { return trig_is_big(x) ? cos_slow(x) : cos_fast(x); }
+
+// ---- trig policies ---------------------------------------------------------------------
+// TrigFast: unconditional fast paths, branch-free; remembers the largest |argument| (high
+// word) it saw.  The integrator runs a whole RK attempt with it as ONE basic block — so the
+// scheduler can overlap the independent polynomial chains of different stages — and tests
+// ok() once at the end; in the (practically never taken) failing case it redoes the attempt
+// with TrigSafe.  TrigSafe: per-call branch to the out-of-line library path.
+struct TrigFast {
+  int big = 0;
+  __device__ __forceinline__ bool ok() const { return big < DM_TRIG_BIG_HI; }
+  __device__ __forceinline__ void sincos(double x, double* s, double* c) {
+    big = max(big, hi_abs(x));
+    sincos_fast(x, s, c);
+  }
+  __device__ __forceinline__ double sin(double x) {
+    big = max(big, hi_abs(x));
+    return sin_fast(x);
+  }
+  __device__ __forceinline__ double cos(double x) {
+    big = max(big, hi_abs(x));
+    return cos_fast(x);
+  }
+  // two independent sincos, polynomial chains interleaved
+  __device__ __forceinline__ void sincos2(double a0, double a1, double* s0, double* c0,
+                                          double* s1, double* c1) {
+    const KC K;
+    big = max(big, max(hi_abs(a0), hi_abs(a1)));
+    int q0, q1;
+    const double r0 = reduce_pio2(K, a0, &q0), r1 = reduce_pio2(K, a1, &q1);
+    const double z0 = r0 * r0, z1 = r1 * r1;
+    double ps0 = fma(DM_S(6), z0, DM_S(5)), ps1 = fma(DM_S(6), z1, DM_S(5));
+    double pc0 = fma(DM_C(6), z0, DM_C(5)), pc1 = fma(DM_C(6), z1, DM_C(5));
+#pragma unroll
+    for (int k = 4; k >= 1; --k) {
+      ps0 = fma(ps0, z0, DM_S(k));
+      ps1 = fma(ps1, z1, DM_S(k));
+      pc0 = fma(pc0, z0, DM_C(k));
+      pc1 = fma(pc1, z1, DM_C(k));
+    }
+    const double sn0 = fma(r0 * z0, ps0, r0), sn1 = fma(r1 * z1, ps1, r1);
+    const double cs0 = fma(z0, fma(z0, pc0, -0.5), 1.0), cs1 = fma(z1, fma(z1, pc1, -0.5), 1.0);
+    *s0 = fix_sin(sn0, cs0, q0);
+    *c0 = fix_cos(sn0, cs0, q0);
+    *s1 = fix_sin(sn1, cs1, q1);
+    *c1 = fix_cos(sn1, cs1, q1);
+  }
+  // NS independent sines (COS: cosines), chains interleaved; out has stride `stride` doubles
+  template <int NS, bool COS>
+  __device__ __forceinline__ void sinN(const double* arg, double* out, int stride) {
+    const KC K;
+    double r[NS], z[NS], ps[NS], pc[NS];
+    int q[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      big = max(big, hi_abs(arg[s]));
+      r[s] = reduce_pio2(K, arg[s], &q[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      z[s] = r[s] * r[s];
+      ps[s] = fma(DM_S(6), z[s], DM_S(5));
+      pc[s] = fma(DM_C(6), z[s], DM_C(5));
+    }
+#pragma unroll
+    for (int k = 4; k >= 1; --k) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        ps[s] = fma(ps[s], z[s], DM_S(k));
+        pc[s] = fma(pc[s], z[s], DM_C(k));
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const double sn = fma(r[s] * z[s], ps[s], r[s]);
+      const double cs = fma(z[s], fma(z[s], pc[s], -0.5), 1.0);
+      out[s * stride] = COS ? fix_cos(sn, cs, q[s]) : fix_sin(sn, cs, q[s]);
+    }
+  }
+};
+
+struct TrigSafe {
+  __device__ __forceinline__ bool ok() const { return true; }
+  __device__ __forceinline__ void sincos(double x, double* s, double* c) { dm::sincos(x, s, c); }
+  __device__ __forceinline__ double sin(double x) { return dm::sin(x); }
+  __device__ __forceinline__ double cos(double x) { return dm::cos(x); }
+  __device__ __forceinline__ void sincos2(double a0, double a1, double* s0, double* c0,
+                                          double* s1, double* c1) {
+    dm::sincos(a0, s0, c0);
+    dm::sincos(a1, s1, c1);
+  }
+  template <int NS, bool COS>
+  __device__ __forceinline__ void sinN(const double* arg, double* out, int stride) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) out[s * stride] = COS ? dm::cos(arg[s]) : dm::sin(arg[s]);
+  }
+};
 
 // 1/x for finite normal x (no special-case handling: used on positive error scales).
 __device__ __forceinline__ double rcp(double x) {

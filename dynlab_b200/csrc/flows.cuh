@@ -111,8 +111,8 @@ DLB_AUTONOMOUS(DLB_FLOW_LORENZ)
 #undef DLB_AUTONOMOUS
 
 // Time part for NS stage times at once (NS = 1 or 5).  tc is [NS][max(N, 1)].
-template <int ID, int NS>
-__device__ __forceinline__ void flow_time(const FlowConsts& fc, const double* t,
+template <int ID, int NS, class Trig>
+__device__ __forceinline__ void flow_time(const FlowConsts& fc, Trig& trig, const double* t,
                                           double (*tc)[FlowTime<ID>::N > 0 ? FlowTime<ID>::N : 1]) {
   const double* c = fc.c;
   if constexpr (ID == DLB_FLOW_DOUBLE_GYRE || ID == DLB_FLOW_DUFFING || ID == DLB_FLOW_PENDULUM ||
@@ -125,41 +125,9 @@ __device__ __forceinline__ void flow_time(const FlowConsts& fc, const double* t,
                      : (ID == DLB_FLOW_HURRICANE) ? c[1]
                                                   : DLB_PI;
     double arg[NS];
-    int big = 0;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-      arg[s] = w * t[s];
-      big = max(big, dm::hi_abs(arg[s]));
-    }
-    if (big >= DM_TRIG_BIG_HI) {  // huge / inf / nan: CUDA's Payne-Hanek path
-#pragma unroll
-      for (int s = 0; s < NS; ++s) tc[s][0] = is_cos ? ::cos(arg[s]) : ::sin(arg[s]);
-    } else {
-      double r[NS], z[NS], ps[NS], pc[NS];
-      int q[NS];
-#pragma unroll
-      for (int s = 0; s < NS; ++s) r[s] = dm::reduce_pio2(arg[s], &q[s]);
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        z[s] = r[s] * r[s];
-        ps[s] = fma(DM_S(6), z[s], DM_S(5));
-        pc[s] = fma(DM_C(6), z[s], DM_C(5));
-      }
-#pragma unroll
-      for (int k = 4; k >= 1; --k) {
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-          ps[s] = fma(ps[s], z[s], DM_S(k));
-          pc[s] = fma(pc[s], z[s], DM_C(k));
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        const double sn = fma(r[s] * z[s], ps[s], r[s]);
-        const double cs = fma(z[s] * z[s], pc[s], fma(-0.5, z[s], 1.0));
-        tc[s][0] = is_cos ? dm::fix_cos(sn, cs, q[s]) : dm::fix_sin(sn, cs, q[s]);
-      }
-    }
+    for (int s = 0; s < NS; ++s) arg[s] = w * t[s];
+    trig.template sinN<NS, is_cos>(arg, &tc[0][0], 1);
   } else if constexpr (FlowTime<ID>::N == 1) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) tc[s][0] = t[s];
@@ -167,49 +135,24 @@ __device__ __forceinline__ void flow_time(const FlowConsts& fc, const double* t,
 }
 
 // Space part.  Y/out have k_flow_info[ID].dim entries.
-template <int ID>
-__device__ __forceinline__ void flow_space(const FlowConsts& fc, const double* tc, const double* Y,
-                                           double* out) {
+template <int ID, class Trig>
+__device__ __forceinline__ void flow_space(const FlowConsts& fc, Trig& trig, const double* tc,
+                                           const double* Y, double* out) {
   const double* c = fc.c;
   const double x = Y[0], y = Y[1];
   if constexpr (ID == DLB_FLOW_DOUBLE_GYRE) {
     const double s = tc[0];  // sin(w t)
     const double a = c[1] * s;
     const double b = 1 - c[2] * s;
-    const double f = a * (x * x) + b * x;
-    const double dfdx = 2 * a * x + b;
-    const double af = DLB_PI * f, ay = y * DLB_PI;
+    const double f = x * fma(a, x, b);       // a x^2 + b x
+    const double dfdx = fma(2 * a, x, b);    // 2 a x + b
     double sf, cf, sy, cy;
-    if (max(dm::hi_abs(af), dm::hi_abs(ay)) >= DM_TRIG_BIG_HI) {
-      ::sincos(af, &sf, &cf);
-      ::sincos(ay, &sy, &cy);
-    } else {  // two interleaved sincos
-      int qf, qy;
-      const double rf = dm::reduce_pio2(af, &qf), ry = dm::reduce_pio2(ay, &qy);
-      const double zf = rf * rf, zy = ry * ry;
-      double psf = fma(DM_S(6), zf, DM_S(5)), psy = fma(DM_S(6), zy, DM_S(5));
-      double pcf = fma(DM_C(6), zf, DM_C(5)), pcy = fma(DM_C(6), zy, DM_C(5));
-#pragma unroll
-      for (int k = 4; k >= 1; --k) {
-        psf = fma(psf, zf, DM_S(k));
-        psy = fma(psy, zy, DM_S(k));
-        pcf = fma(pcf, zf, DM_C(k));
-        pcy = fma(pcy, zy, DM_C(k));
-      }
-      const double snf = fma(rf * zf, psf, rf), sny = fma(ry * zy, psy, ry);
-      const double csf = fma(zf * zf, pcf, fma(-0.5, zf, 1.0));
-      const double csy = fma(zy * zy, pcy, fma(-0.5, zy, 1.0));
-      sf = dm::fix_sin(snf, csf, qf);
-      cf = dm::fix_cos(snf, csf, qf);
-      sy = dm::fix_sin(sny, csy, qy);
-      cy = dm::fix_cos(sny, csy, qy);
-    }
+    trig.sincos2(DLB_PI * f, y * DLB_PI, &sf, &cf, &sy, &cy);
     out[0] = c[3] * sf * cy;
     out[1] = c[4] * cf * sy * dfdx;
   } else if constexpr (ID == DLB_FLOW_AUTONOMOUS_DOUBLE_GYRE) {
     double sx, cx, sy, cy;
-    dm::sincos(DLB_PI * x, &sx, &cx);
-    dm::sincos(y * DLB_PI, &sy, &cy);
+    trig.sincos2(DLB_PI * x, y * DLB_PI, &sx, &cx, &sy, &cy);
     out[0] = -DLB_PI * sx * cy;
     out[1] = DLB_PI * cx * sy;
   } else if constexpr (ID == DLB_FLOW_BICKLEY_JET) {
@@ -218,15 +161,14 @@ __device__ __forceinline__ void flow_space(const FlowConsts& fc, const double* t
     const double ch = 1 / cosh(yl);
     const double sech2 = ch * ch, th = tanh(yl);
     double s3, c3, s2, c2;
-    dm::sincos(c[5] * (x - c[3] * t), &s3, &c3);
-    dm::sincos(c[4] * (x - c[2] * t), &s2, &c2);
+    trig.sincos2(c[5] * (x - c[3] * t), c[4] * (x - c[2] * t), &s3, &c3, &s2, &c2);
     out[0] = c[0] * sech2 + c[6] * th * sech2 * c3 + c[7] * th * sech2 * c2;
     out[1] = c[8] * sech2 * s3 - c[9] * sech2 * s2;
   } else if constexpr (ID == DLB_FLOW_GLIDER) {
     const double r = sqrt(x * x + y * y);
     const double th2 = -2 * atan2(y, x);
     double s, cs;
-    dm::sincos(th2, &s, &cs);
+    trig.sincos(th2, &s, &cs);
     s = 1.2 * s;
     cs = 1.4 - cs;
     out[0] = r * (-y * s - cs * x);
@@ -245,7 +187,7 @@ __device__ __forceinline__ void flow_space(const FlowConsts& fc, const double* t
     out[1] = x - x * x * x - c[1] * y + c[0] * tc[0];
   } else if constexpr (ID == DLB_FLOW_PENDULUM) {  // A, gamma, omega; tc = sin(omega t)
     out[0] = y;
-    out[1] = -dm::sin(x) - c[1] * y + c[0] * tc[0];
+    out[1] = -trig.sin(x) - c[1] * y + c[0] * tc[0];
   } else if constexpr (ID == DLB_FLOW_HURRICANE) {  // tc = cos(eye_omega t)
     const double yt = y - c[4];
     const double den = x * x + yt * yt + c[0];
@@ -256,7 +198,7 @@ __device__ __forceinline__ void flow_space(const FlowConsts& fc, const double* t
     out[1] = c[1] * (1 - x * x) * y - x - c[2] * y + c[0] * tc[0];
   } else if constexpr (ID == DLB_FLOW_BEAD) {  // 1/epsilon, gamma
     double s, cs;
-    dm::sincos(x, &s, &cs);
+    trig.sincos(x, &s, &cs);
     out[0] = y;
     out[1] = c[0] * (s * (c[1] * cs - 1) - y);
   } else if constexpr (ID == DLB_FLOW_LOTKA_VOLTERRA) {  // alpha, beta, gamma, delta
@@ -266,9 +208,8 @@ __device__ __forceinline__ void flow_space(const FlowConsts& fc, const double* t
     const double z = Y[2];
     const double At = c[1] + c[0] * tc[0];
     double sx, cx, sy, cy, sz, cz;
-    dm::sincos(x, &sx, &cx);
-    dm::sincos(y, &sy, &cy);
-    dm::sincos(z, &sz, &cz);
+    trig.sincos2(x, y, &sx, &cx, &sy, &cy);
+    trig.sincos(z, &sz, &cz);
     out[0] = At * sz + c[3] * cy;
     out[1] = c[2] * sx + At * cz;
     out[2] = c[3] * sy + c[2] * cx;
@@ -284,9 +225,10 @@ __device__ __forceinline__ void flow_space(const FlowConsts& fc, const double* t
 template <int ID>
 __device__ __forceinline__ void flow_rhs(const FlowConsts& fc, double t, const double* Y,
                                          double* out) {
+  dm::TrigSafe trig;
   double tc[1][FlowTime<ID>::N > 0 ? FlowTime<ID>::N : 1];
-  flow_time<ID, 1>(fc, &t, tc);
-  flow_space<ID>(fc, tc[0], Y, out);
+  flow_time<ID, 1>(fc, trig, &t, tc);
+  flow_space<ID>(fc, trig, tc[0], Y, out);
 }
 
 // Run the statement block with `constexpr int ID` bound to the runtime flow id.

@@ -24,6 +24,9 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int RK_BLOCK = 128;
+#ifndef DLB_RK_MINBLOCKS
+#define DLB_RK_MINBLOCKS 5
+#endif
 
 // Dormand-Prince tableau exactly as scipy states it (rk.py:541-552); B[1] = E[1] = 0.
 // Kept in __constant__ memory (see dmath.cuh: literals would cost two UMOVs per use).
@@ -117,20 +120,86 @@ __device__ __forceinline__ double rms_norm(const double* v) {
   return sqrt(s) * (N == 2 ? 0.70710678118654752440 : 0.57735026918962576451);
 }
 
+// The six stage evaluations of one attempt (rk_step, rk.py:60-69) for state (t, y, f = K0)
+// and step h.  Stage times are evaluated first in one block; stages 6 and 7 share t + h
+// (C[5] = 1).  Returns K1..K6 (K6 = f_new) and y_new.
+template <int N>
+struct StageOut {
+  double K[6][N];
+  double yn[N];
+};
+
+template <int ID, int N, class Trig>
+__device__ __forceinline__ void rk_stages(const FlowConsts& fc, Trig& trig, double t, double h,
+                                          const double* y, const double* f, StageOut<N>& o) {
+  constexpr int NT = FlowTime<ID>::N > 0 ? FlowTime<ID>::N : 1;
+  double ts[5], tc[5][NT], ys[N];
+  ts[0] = fma(C1, h, t);
+  ts[1] = fma(C2, h, t);
+  ts[2] = fma(C3, h, t);
+  ts[3] = fma(C4, h, t);
+  ts[4] = t + h;
+  flow_time<ID, 5>(fc, trig, ts, tc);
+  double(*K)[N] = o.K;
+#pragma unroll
+  for (int i = 0; i < N; ++i) ys[i] = fma(f[i] * A10, h, y[i]);
+  flow_space<ID>(fc, trig, tc[0], ys, K[0]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) ys[i] = fma(fma(K[0][i], A21, f[i] * A20), h, y[i]);
+  flow_space<ID>(fc, trig, tc[1], ys, K[1]);
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    ys[i] = fma(fma(K[1][i], A32, fma(K[0][i], A31, f[i] * A30)), h, y[i]);
+  flow_space<ID>(fc, trig, tc[2], ys, K[2]);
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    ys[i] = fma(fma(K[2][i], A43, fma(K[1][i], A42, fma(K[0][i], A41, f[i] * A40))), h, y[i]);
+  flow_space<ID>(fc, trig, tc[3], ys, K[3]);
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    ys[i] = fma(
+        fma(K[3][i], A54, fma(K[2][i], A53, fma(K[1][i], A52, fma(K[0][i], A51, f[i] * A50)))),
+        h, y[i]);
+  flow_space<ID>(fc, trig, tc[4], ys, K[4]);
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    o.yn[i] = fma(
+        h, fma(K[4][i], B5, fma(K[3][i], B4, fma(K[2][i], B3, fma(K[1][i], B2, f[i] * B0)))),
+        y[i]);
+  flow_space<ID>(fc, trig, tc[4], o.yn, K[5]);  // f_new
+}
+
+// Out-of-line redo of an attempt whose fast trigonometry saw a huge / non-finite argument.
+template <int ID, int N>
+__device__ __noinline__ StageOut<N> rk_stages_safe(const FlowConsts& fc, double t, double h,
+                                                   StageOut<1> yv, StageOut<1> fv) {
+  // (y and f travel by value inside small structs: yv.K[i][0] = y[i], fv.K[i][0] = f[i])
+  double y[N], f[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    y[i] = yv.K[i][0];
+    f[i] = fv.K[i][0];
+  }
+  dm::TrigSafe trig;
+  StageOut<N> o;
+  rk_stages<ID, N>(fc, trig, t, h, y, f, o);
+  return o;
+}
+
 // |nextafter(t, dir * inf) - t| (rk.py:119) from the bit pattern: the spacing of doubles
 // at t in the direction of integration.
 __device__ __forceinline__ double ulp_towards(double t, double dir) {
+  // t is finite here: t0 and tf are validated on the host and t stays between them.
   const long long b = __double_as_longlong(t);
-  const long long mag = b & 0x7fffffffffffffffLL;
-  if (mag >= 0x7ff0000000000000LL) return fabs(nextafter(t, dir * CUDART_INF) - t);  // inf / nan
-  if (mag == 0) return 4.9406564584124654e-324;  // nextafter(0, +-inf) = +-denorm_min
-  const bool away = ((b < 0) == (dir < 0));      // moving away from zero?
+  const bool away = ((b < 0) == (dir < 0));  // moving away from zero?
   const double nb = __longlong_as_double(away ? b + 1 : b - 1);
-  return fabs(nb - t);
+  const double d = fabs(nb - t);
+  // t == +-0: nextafter(0, +-inf) = +-denorm_min
+  return ((b & 0x7fffffffffffffffLL) == 0) ? 4.9406564584124654e-324 : d;
 }
 
 template <int ID, int N, bool GRID>
-__global__ void __launch_bounds__(RK_BLOCK) rk45_kernel(const Rk45Params P) {
+__global__ void __launch_bounds__(RK_BLOCK, DLB_RK_MINBLOCKS) rk45_kernel(const Rk45Params P) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
   const double dir = P.direction;
@@ -264,43 +333,23 @@ __global__ void __launch_bounds__(RK_BLOCK) rk45_kernel(const Rk45Params P) {
         h = t_new - t;
         h_abs = fabs(h);
 
-        // time parts of all stages in one block; stages 6 and 7 share t + h (C[5] = 1)
-        constexpr int NT = FlowTime<ID>::N > 0 ? FlowTime<ID>::N : 1;
-        double ts[5], tc[5][NT];
-        ts[0] = fma(C1, h, t);
-        ts[1] = fma(C2, h, t);
-        ts[2] = fma(C3, h, t);
-        ts[3] = fma(C4, h, t);
-        ts[4] = t + h;
-        flow_time<ID, 5>(P.fc, ts, tc);
-
-        // rk_step, rk.py:60-69.  K0 = f (FSAL)
-        double K1[N], K2[N], K3[N], K4[N], K5[N], K6[N], ys[N], yn[N];
+        // rk_step with branch-free trigonometry; one validity test for the whole attempt
+        StageOut<N> so;
+        {
+          dm::TrigFast trig;
+          rk_stages<ID, N>(P.fc, trig, t, h, y, f, so);
+          if (!trig.ok()) {
+            StageOut<1> yv, fv;
 #pragma unroll
-        for (int i = 0; i < N; ++i) ys[i] = fma(f[i] * A10, h, y[i]);
-        flow_space<ID>(P.fc, tc[0], ys, K1);
-#pragma unroll
-        for (int i = 0; i < N; ++i) ys[i] = fma(fma(K1[i], A21, f[i] * A20), h, y[i]);
-        flow_space<ID>(P.fc, tc[1], ys, K2);
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-          ys[i] = fma(fma(K2[i], A32, fma(K1[i], A31, f[i] * A30)), h, y[i]);
-        flow_space<ID>(P.fc, tc[2], ys, K3);
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-          ys[i] = fma(fma(K3[i], A43, fma(K2[i], A42, fma(K1[i], A41, f[i] * A40))), h, y[i]);
-        flow_space<ID>(P.fc, tc[3], ys, K4);
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-          ys[i] = fma(
-              fma(K4[i], A54, fma(K3[i], A53, fma(K2[i], A52, fma(K1[i], A51, f[i] * A50)))), h,
-              y[i]);
-        flow_space<ID>(P.fc, tc[4], ys, K5);
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-          yn[i] = fma(
-              h, fma(K5[i], B5, fma(K4[i], B4, fma(K3[i], B3, fma(K2[i], B2, f[i] * B0)))), y[i]);
-        flow_space<ID>(P.fc, tc[4], yn, K6);  // f_new
+            for (int i = 0; i < N; ++i) {
+              yv.K[i][0] = y[i];
+              fv.K[i][0] = f[i];
+            }
+            so = rk_stages_safe<ID, N>(P.fc, t, h, yv, fv);
+          }
+        }
+        const double(*K)[N] = so.K;
+        const double* yn = so.yn;
         nfev_l += 6;
 
         // error estimate, rk.py:105-109,146-147; s = error_norm^2 (no square root needed:
@@ -310,8 +359,9 @@ __global__ void __launch_bounds__(RK_BLOCK) rk45_kernel(const Rk45Params P) {
         for (int i = 0; i < N; ++i) {
           const double sc = P.atol[i] + fmax(fabs(y[i]), fabs(yn[i])) * rtol;
           const double ee =
-              fma(K6[i], E6,
-                  fma(K5[i], E5, fma(K4[i], E4, fma(K3[i], E3, fma(K2[i], E2, f[i] * E0)))));
+              fma(K[5][i], E6,
+                  fma(K[4][i], E5,
+                      fma(K[3][i], E4, fma(K[2][i], E3, fma(K[1][i], E2, f[i] * E0)))));
           const double e = ee * h * dm::rcp(sc);
           ssum = fma(e, e, ssum);
         }
@@ -331,7 +381,7 @@ __global__ void __launch_bounds__(RK_BLOCK) rk45_kernel(const Rk45Params P) {
 #pragma unroll
           for (int i = 0; i < N; ++i) {
             y[i] = yn[i];
-            f[i] = K6[i];
+            f[i] = K[5][i];
           }
           fresh = true;
           c_acc += 1;
@@ -394,6 +444,10 @@ int fill_common(Rk45Params& P, int flow_id, const double* h_params, int n_params
                 double tf, double rtol, double max_step, double first_step) {
   if (!flow_prepare(flow_id, h_params, n_params, &P.fc)) {
     dlb_set_error("unknown flow id %d or wrong parameter count %d", flow_id, n_params);
+    return DLB_ERR_ARG;
+  }
+  if (!isfinite(t0) || !isfinite(tf)) {
+    dlb_set_error("t0 and tf must be finite");
     return DLB_ERR_ARG;
   }
   if (!(max_step > 0)) {  // common.py:19-23 validate_max_step
