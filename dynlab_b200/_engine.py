@@ -79,7 +79,10 @@ class Engine:
     def workspace(self, xdim: int, ydim: int):
         need = int(nat.lib.dlb_workspace_bytes(xdim, ydim))
         if self._workspace is None or self._workspace.numel() < need:
-            self._workspace = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=self.device)
+            # allocate the new block while the old one is still alive, so that the address
+            # changes (the library caches stencil coefficients per workspace address)
+            grown = torch.empty(max(need, 1 << 22), dtype=torch.uint8, device=self.device)
+            self._workspace = grown
         return self._workspace.data_ptr(), self._workspace.numel()
 
     def empty(self, *shape, dtype=_F64):
@@ -149,7 +152,7 @@ class Engine:
                 out = self.empty(out_rows, xdim)
             xi = self.empty(out_rows, xdim, 2) if xi_mode != nat.XI_NONE else None
             ws, wsz = self.workspace(xdim, ydim)
-            with self._timed("ftle_stencil"):
+            with self._timed("ftle_stencil", 2):
               nat.check(nat.lib.dlb_ftle_stencil(
                 fm_local.data_ptr(), nloc, grow0, nat.dptr(x), xdim, nat.dptr(y), ydim,
                 int(edge_order), float(t_span), out_row0, out_rows, out.data_ptr(),
@@ -167,7 +170,7 @@ class Engine:
             mask = self.empty(out_rows, xdim, dtype=torch.uint8) if need_mask else None
             xi = self.empty(out_rows, xdim, 2) if xi_mode != nat.XI_NONE else None
             ws, wsz = self.workspace(xdim, ydim)
-            with self._timed("euler_stencil"):
+            with self._timed("euler_stencil", 2):
               nat.check(nat.lib.dlb_euler_stencil(
                 mode, u_local.data_ptr(), v_local.data_ptr(), nloc, grow0, nat.dptr(x), xdim,
                 nat.dptr(y), ydim, int(edge_order), out_row0, out_rows, int(bool(negate)),

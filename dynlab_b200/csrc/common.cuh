@@ -31,3 +31,9 @@ void dlb_set_error(const char* fmt, ...);
 // dlb_workspace_bytes(xdim, ydim) bytes); kernels use it for coordinate/coefficient arrays
 // and the work-stealing counter.
 static inline size_t dlb_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// The stencil entry points keep their per-axis coefficient arrays in the caller's workspace
+// and skip the rebuild + upload when the same (x, y, edge_order) come again (stencil.cu:
+// setup_axes).  Entry points that write the x / y region of a workspace with another grid
+// shape call this so that a stale cache entry is never trusted.
+void dlb_axes_cache_note_layout(const void* d_workspace, int64_t xdim, int64_t ydim);

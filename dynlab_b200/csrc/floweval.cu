@@ -115,6 +115,7 @@ extern "C" int dlb_flow_eval_grid(int flow_id, const double* h_params, int n_par
   if (xdim == 0 || ydim == 0) return DLB_OK;
   double* d_x = (double*)((char*)d_workspace + 256);
   double* d_y = d_x + xdim;
+  dlb_axes_cache_note_layout(d_workspace, xdim, ydim);
   DLB_CUDA_CHECK(cudaMemcpyAsync(d_x, h_x, sizeof(double) * xdim, cudaMemcpyHostToDevice, stream));
   DLB_CUDA_CHECK(cudaMemcpyAsync(d_y, h_y, sizeof(double) * ydim, cudaMemcpyHostToDevice, stream));
   P.t = t;

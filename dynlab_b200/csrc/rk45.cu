@@ -25,7 +25,7 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int RK_BLOCK = 128;
 #ifndef DLB_RK_MINBLOCKS
-#define DLB_RK_MINBLOCKS 5
+#define DLB_RK_MINBLOCKS 4
 #endif
 
 // Dormand-Prince tableau exactly as scipy states it (rk.py:541-552); B[1] = E[1] = 0.
@@ -515,6 +515,7 @@ extern "C" int dlb_flowmap_rk45(int flow_id, const double* h_params, int n_param
   char* ws = (char*)d_workspace;
   double* d_x = (double*)(ws + 256);
   double* d_y = d_x + xdim;
+  dlb_axes_cache_note_layout(d_workspace, xdim, rows);
   DLB_CUDA_CHECK(cudaMemsetAsync(ws, 0, 256, stream));
   DLB_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, sizeof(uint64_t) * DLB_CNT_WORDS, stream));
   if (rows == 0) return DLB_OK;

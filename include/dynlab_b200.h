@@ -91,7 +91,11 @@ int dlb_flow_dim(int flow_id);        /* 2 or 3; <0 if unknown */
 int dlb_flow_nparams(int flow_id);    /* number of keyword parameters */
 const char* dlb_flow_name(int flow_id);
 
-/* Bytes of device workspace the grid entry points need for a (xdim, ydim) grid. */
+/* Bytes of device workspace the grid entry points need for a (xdim, ydim) grid.
+ * The workspace is scratch owned by the caller but written only by this library: the stencil
+ * entry points keep their per-axis coefficient arrays in it and skip the rebuild + upload when
+ * the same (workspace, x, y, edge_order) come again, so the caller must not modify it between
+ * calls (freeing it is fine). */
 size_t dlb_workspace_bytes(int64_t xdim, int64_t ydim);
 
 /* K0 — evaluate a flow on points or on meshgrid(x, y).
