@@ -170,6 +170,10 @@ class LagrangianDiagnostic2D(Diagnostic2D, ABC):
         if not num_threads >= 1:
             raise ValueError("num_threads must be an integer greater than 0.")
         self.stats = {}
+        # Multi-GPU: all-gather the full flow map on every rank after the integration (what the
+        # reference's `flow_map` attribute holds).  compute_device() of FTLE switches it off —
+        # the stencil only needs the 1-row halo — and leaves `flow_map` as this rank's rows.
+        self.gather_flow_map = True
 
     def _tolerances(self, kwargs):
         if self.integrator is odeint_wrapper:
@@ -220,12 +224,19 @@ class LagrangianDiagnostic2D(Diagnostic2D, ABC):
             eng.flow_map(fid, params, self._xf, self._yf, slab.row0, slab.rows, t0, tf,
                          kw["rtol"], float(atol), kw["max_step"], first or 0.0, out=own)
         self._counters_pending = slab.rows > 0
+        own = local[slab.halo_lo:slab.halo_lo + slab.rows]
         if size > 1:
             sharding.exchange_halo(local, slab, self.ydim, rank, size)
-            pad = torch.zeros(slab.rows_max, self.xdim, 2, dtype=torch.float64, device=eng.device)
-            if slab.rows:
-                pad[:slab.rows] = local[slab.halo_lo:slab.halo_lo + slab.rows]
-            self.flow_map = sharding.gather_rows(pad, self.ydim, size)
+            if self.gather_flow_map:
+                if slab.rows == slab.rows_max:
+                    pad = own  # contiguous row block: gather straight from it
+                else:
+                    pad = torch.empty(slab.rows_max, self.xdim, 2, dtype=torch.float64,
+                                      device=eng.device)
+                    pad[:slab.rows] = own
+                self.flow_map = sharding.gather_rows(pad, self.ydim, size)
+            else:
+                self.flow_map = own
         else:
             self.flow_map = local[:slab.nloc]
         return local, slab

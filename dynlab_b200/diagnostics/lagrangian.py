@@ -26,14 +26,14 @@ def _ftle_on_device(diag, local, slab, t, edge_order, xi_mode):
     if size == 1:
         return eng.ftle_stencil(local, 0, diag._xf, diag._yf, edge_order, t_span, 0, diag.ydim,
                                 xi_mode)
-    out = torch.zeros(slab.rows_max, diag.xdim, dtype=torch.float64, device=eng.device)
+    out = torch.empty(slab.rows_max, diag.xdim, dtype=torch.float64, device=eng.device)
     xi = None
     if slab.rows:
         _, xi = eng.ftle_stencil(local, slab.lo, diag._xf, diag._yf, edge_order, t_span,
                                  slab.row0, slab.rows, xi_mode, out=out[:slab.rows])
     field = sharding.gather_rows(out, diag.ydim, size)
     if xi_mode != nat.XI_NONE:
-        pad = torch.zeros(slab.rows_max, diag.xdim, 2, dtype=torch.float64, device=eng.device)
+        pad = torch.empty(slab.rows_max, diag.xdim, 2, dtype=torch.float64, device=eng.device)
         if xi is not None:
             pad[:slab.rows] = xi
         xi = sharding.gather_rows(pad, diag.ydim, size)
@@ -50,15 +50,23 @@ class FTLE(LagrangianDiagnostic2D):
         """Returns ``np.ma.MaskedArray[ydim, xdim]``; sets ``x, y, xdim, ydim, flow_map,
         field`` like the reference.  ``kwargs`` (rtol, atol, max_step, first_step) go to the
         integrator."""
-        field = self.compute_device(x, y, f, t, edge_order, **kwargs)
+        field = self._run(x, y, f, t, edge_order, self.gather_flow_map, kwargs)
         self.field = np.ma.MaskedArray(Engine.get().to_host(field))
         self._collect_stats()
         return self.field
 
     def compute_device(self, x, y, f, t, edge_order: int = 1, **kwargs):
         """Same computation, result left on the device (``torch.Tensor[ydim, xdim]``, also kept
-        as ``field_device``); nothing is synchronised or copied to the host."""
-        local, slab = super().compute(x, y, f, t, **kwargs)
+        as ``field_device``); nothing is synchronised or copied to the host.  Under multi-GPU
+        sharding the flow map is not gathered: ``flow_map`` holds this rank's rows only."""
+        return self._run(x, y, f, t, edge_order, False, kwargs)
+
+    def _run(self, x, y, f, t, edge_order, gather_flow_map, kwargs):
+        keep, self.gather_flow_map = self.gather_flow_map, gather_flow_map
+        try:
+            local, slab = super().compute(x, y, f, t, **kwargs)
+        finally:
+            self.gather_flow_map = keep
         field, _ = _ftle_on_device(self, local, slab, t, edge_order, nat.XI_NONE)
         self.field_device = field
         return field

@@ -100,7 +100,10 @@ def gather_rows(own_padded: torch.Tensor, ydim: int, size: int) -> torch.Tensor:
     rows_max = own_padded.shape[0]
     tail = tuple(own_padded.shape[1:])
     buf = torch.empty((size, rows_max) + tail, dtype=own_padded.dtype, device=own_padded.device)
-    dist.all_gather(list(buf.unbind(0)), own_padded.contiguous())
+    if own_padded.is_cuda:
+        dist.all_gather_into_tensor(buf, own_padded.contiguous())  # one NCCL all-gather, no copies
+    else:  # gloo (CPU tests)
+        dist.all_gather(list(buf.unbind(0)), own_padded.contiguous())
     n = active_ranks(ydim, size)
     if n == size and ydim == size * rows_max:
         return buf.view((ydim,) + tail)
