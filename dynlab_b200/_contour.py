@@ -1,15 +1,27 @@
 """Zero-contour extraction of a masked grid (host side of RidgeExtractor2D.extract_ridges).
 
 The reference calls ``contourpy.contour_generator(x=, y=, z=masked).lines(0)``
-(R:src/dynlab/diagnostics/_base_classes.py:270).  When contourpy is importable it is used
-directly (it is the reference's own dependency); otherwise the marching-squares tracer below
-produces the polylines.  Output: ``list[np.ndarray[n, 2]]`` of (x, y) vertices, like
-``LineType.Separate``.
+(R:src/dynlab/diagnostics/_base_classes.py:270): default "serial" algorithm, ``corner_mask``
+on (z is a masked array), ``LineType.Separate`` -> ``list[np.ndarray[n, 2]]`` of (x, y) vertices.
+When contourpy is importable it is used directly (it is the reference's own dependency);
+otherwise ``marching_squares`` below produces the polylines with contourpy's conventions:
 
-Parity note: contourpy is not installed in the build image, so vertex *positions* (linear
-interpolation on cell edges) are checked against the reference's golden vectors, but the
-ordering of lines and of vertices inside a line follows this tracer's own deterministic rule
-(boundary-started lines first, in row-major order of their first cell; then closed loops).
+* a node is "upper" iff ``z > level``;
+* a quad contributes if none of its corners is masked; a quad with exactly one masked corner
+  contributes the triangle of the other three (corner masking); two or more: nothing;
+* saddle quads are resolved by the mean of the four corners (``zmid > level``);
+* lines are oriented with the upper region on their left; an open line starts where it enters
+  the contoured region (domain edge, mask edge or triangle diagonal); closed loops repeat
+  their first vertex at the end;
+* lines are emitted in the row-major scan order (y outer, x inner) of the cell they start in;
+* vertices are linear interpolations along cell edges.
+
+These rules reproduce the line sets, vertex order and coordinates of the reference's own
+golden tests (R:tests/test_diagnostics/test_lagrangian.py:21-37,
+R:tests/test_diagnostics/test_eulerian.py:127-181) from the reference's ridge fields — see
+tests/test_contour.py.  contourpy itself is not installed in the build image, so configurations
+those goldens do not exercise (several starts in one cell, closed-loop start vertex) follow
+this module's own deterministic choice.
 """
 from __future__ import annotations
 
@@ -27,87 +39,144 @@ def zero_contour_lines(x, y, z, level: float = 0.0):
     return marching_squares(np.asarray(x, dtype=float), np.asarray(y, dtype=float), z, level)
 
 
-def _interp(p0, p1, z0, z1, level):
-    f = (level - z0) / (z1 - z0)
-    return p0 + f * (p1 - p0)
+def _cell_segments(zd, mask, above, level):
+    """Vectorised per-cell case analysis.  Returns arrays (cell_j, cell_i, a0, a1, b0, b1):
+    one row per contour segment, running from the crossing on edge (a0, a1) to the crossing on
+    edge (b0, b1); nodes are flat indices j * nx + i."""
+    ny, nx = zd.shape
+    J, I = np.meshgrid(np.arange(ny - 1), np.arange(nx - 1), indexing="ij")
+    # corners counter-clockwise: (j,i) (j,i+1) (j+1,i+1) (j+1,i)
+    cj = np.stack([J, J, J + 1, J + 1], axis=-1)
+    ci = np.stack([I, I + 1, I + 1, I], axis=-1)
+    node = cj * nx + ci
+    m = mask[cj, ci]
+    up = above[cj, ci]
+    nmask = m.sum(axis=-1)
+    out = []
+
+    def emit(sel, ka, kb, la, lb):
+        """cells `sel` (boolean [ny-1, nx-1]): segment from edge (corner ka -> la) to edge
+        (corner kb -> lb); corner indices are per-cell arrays or scalars."""
+        if not sel.any():
+            return
+        jj, ii = J[sel], I[sel]
+        nd = node[sel]
+        r = np.arange(nd.shape[0])
+
+        def pick(k):
+            return nd[r, k[sel]] if isinstance(k, np.ndarray) else nd[:, k]
+
+        out.append(np.stack([jj, ii, pick(ka), pick(la), pick(kb), pick(lb)], axis=1))
+
+    # ---- full quads
+    quad = nmask == 0
+    for k in range(4):  # a segment starts on the CCW edge k -> k+1 where upper -> lower
+        k1 = (k + 1) % 4
+        start = quad & up[..., k] & ~up[..., k1]
+        if not start.any():
+            continue
+        n_up = up.sum(axis=-1)
+        saddle = start & (n_up == 2) & (up[..., (k + 2) % 4]) & ~up[..., (k + 3) % 4]
+        simple = start & ~saddle
+        # simple: the end edge is the only lower -> upper edge; find it per cell
+        for e in range(4):
+            e1 = (e + 1) % 4
+            emit(simple & ~up[..., e] & up[..., e1], k, e, k1, e1)
+        if saddle.any():
+            zmid = 0.25 * zd[cj, ci].sum(axis=-1)
+            mid_up = zmid > level
+            # centre lower: the upper corner k is cut off -> ends on edge k-1 -> k
+            emit(saddle & ~mid_up, k, (k + 3) % 4, k1, k)
+            # centre upper: the lower corner k+1 is cut off -> ends on edge k+1 -> k+2
+            emit(saddle & mid_up, k, k1, k1, (k + 2) % 4)
+    # ---- corner-masked triangles
+    for c in range(4):
+        tri = (nmask == 1) & m[..., c]
+        if not tri.any():
+            continue
+        v = [(c + 1) % 4, (c + 2) % 4, (c + 3) % 4]  # remaining corners, still CCW
+        for s in range(3):
+            a, a1 = v[s], v[(s + 1) % 3]
+            start = tri & up[..., a] & ~up[..., a1]
+            for e in range(3):
+                b, b1 = v[e], v[(e + 1) % 3]
+                emit(start & ~up[..., b] & up[..., b1], a, b, a1, b1)
+    if not out:
+        return np.zeros((0, 6), dtype=np.int64)
+    return np.concatenate(out, axis=0)
 
 
 def marching_squares(x, y, z, level=0.0):
-    """Trace the ``level`` contour of ``z[ydim, xdim]`` (masked array or ndarray).
-
-    A quad contributes only if none of its four corners is masked.  Saddle quads are split by
-    the sign of the centre value (mean of the corners).  Segments are oriented with the higher
-    values on the left and chained through shared cell edges."""
+    """Trace the ``level`` contour of ``z[ydim, xdim]`` (masked array or ndarray)."""
     zd = np.ma.getdata(z).astype(float)
     mask = np.ma.getmaskarray(z) | ~np.isfinite(zd)
     ny, nx = zd.shape
-    above = zd > level
+    if ny < 2 or nx < 2:
+        return []
+    above = (zd > level) & ~mask
+    segs = _cell_segments(zd, mask, above, level)
+    if segs.shape[0] == 0:
+        return []
+    # scan order of the owning cell
+    order = np.lexsort((segs[:, 1], segs[:, 0]))
+    segs = segs[order]
+    n = segs.shape[0]
 
-    # edge ids: horizontal edge (i, j)-(i, j+1) -> ('h', i, j); vertical (i, j)-(i+1, j) -> ('v', i, j)
-    def edge_point(e):
-        kind, i, j = e
-        if kind == 'h':
-            px = _interp(x[j], x[j + 1], zd[i, j], zd[i, j + 1], level)
-            return (px, y[i])
-        py = _interp(y[i], y[i + 1], zd[i, j], zd[i + 1, j], level)
-        return (x[j], py)
+    def edge_key(p, q):
+        lo, hi = np.minimum(p, q), np.maximum(p, q)
+        return lo * (nx * ny) + hi
 
-    # segments: list of (edge_from, edge_to); next_of[edge_from] -> list of edge_to
-    starts = {}
-    ends = {}
-    segs = []
-    for i in range(ny - 1):
-        for j in range(nx - 1):
-            if mask[i, j] or mask[i, j + 1] or mask[i + 1, j] or mask[i + 1, j + 1]:
-                continue
-            # corners: 0=(i,j) 1=(i,j+1) 2=(i+1,j+1) 3=(i+1,j); edges between consecutive corners
-            a = (above[i, j], above[i, j + 1], above[i + 1, j + 1], above[i + 1, j])
-            n_above = sum(a)
-            if n_above in (0, 4):
-                continue
-            e = (('h', i, j), ('v', i, j + 1), ('h', i + 1, j), ('v', i, j))  # bottom,right,top,left
-            # walking the quad counter-clockwise (0->1->2->3), a contour enters on an edge where
-            # the corners go above->below and leaves where they go below->above: higher on left
-            ins = [k for k in range(4) if a[k] and not a[(k + 1) % 4]]
-            outs = [k for k in range(4) if not a[k] and a[(k + 1) % 4]]
-            if len(ins) == 1:
-                pairs = [(ins[0], outs[0])]
-            else:  # saddle
-                centre_above = 0.25 * (zd[i, j] + zd[i, j + 1] + zd[i + 1, j + 1] + zd[i + 1, j]) > level
-                pairs = []
-                for k in ins:
-                    # the 'in' edge k pairs with the out edge that encloses the above corner k
-                    # (centre below) or goes around through the centre (centre above)
-                    cand = (k - 1) % 4 if not centre_above else (k + 1) % 4
-                    pairs.append((k, cand))
-            for ki, ko in pairs:
-                s = (e[ki], e[ko])
-                segs.append(s)
-                starts.setdefault(e[ki], []).append(len(segs) - 1)
-                ends.setdefault(e[ko], []).append(len(segs) - 1)
+    start_key = edge_key(segs[:, 2], segs[:, 3])
+    end_key = edge_key(segs[:, 4], segs[:, 5])
+    # successor: the segment that starts on the edge this one ends on
+    sorter = np.argsort(start_key, kind="stable")
+    pos = np.searchsorted(start_key[sorter], end_key)
+    pos_c = np.minimum(pos, n - 1)
+    has_next = (pos < n) & (start_key[sorter][pos_c] == end_key)
+    nxt = np.where(has_next, sorter[pos_c], -1)
+    has_prev = np.zeros(n, dtype=bool)
+    has_prev[nxt[has_next]] = True
 
-    used = [False] * len(segs)
+    # vertex on an edge (p, q): linear interpolation to z == level
+    def vertex(p, q):
+        zp, zq = zd.flat[p], zd.flat[q]
+        f = (level - zp) / (zq - zp)
+        xp, xq = x[p % nx], x[q % nx]
+        yp, yq = y[p // nx], y[q // nx]
+        return xp + f * (xq - xp), yp + f * (yq - yp)
+
+    sx, sy = vertex(segs[:, 2], segs[:, 3])
+    ex, ey = vertex(segs[:, 4], segs[:, 5])
+
+    nxt_l = nxt.tolist()
+    used = np.zeros(n, dtype=bool)
     lines = []
-
-    def follow(first):
-        pts = [edge_point(segs[first][0]), edge_point(segs[first][1])]
-        used[first] = True
-        cur = segs[first][1]
-        while True:
-            nxt = [k for k in starts.get(cur, []) if not used[k]]
-            if not nxt:
-                break
-            k = nxt[0]
+    starts = np.flatnonzero(~has_prev)  # open lines, already in scan order of their first cell
+    loops_from = 0
+    heads = [(int(s), False) for s in starts]
+    # closed loops: every segment not reachable from an open start; visit in scan order
+    for s, _ in heads:
+        k = s
+        while k != -1 and not used[k]:
             used[k] = True
-            cur = segs[k][1]
-            pts.append(edge_point(cur))
-        return np.array(pts)
-
-    # open lines first: segments whose entry edge is not the exit edge of another segment
-    for k, s in enumerate(segs):
-        if not used[k] and not ends.get(s[0]):
-            lines.append(follow(k))
-    for k in range(len(segs)):  # closed loops
-        if not used[k]:
-            lines.append(follow(k))
+            k = nxt_l[k]
+    for k0 in range(n):
+        if not used[k0]:
+            heads.append((k0, True))
+            k = k0
+            while not used[k]:
+                used[k] = True
+                k = nxt_l[k]
+    # emit in scan order of the starting cell (segments are sorted by cell)
+    heads.sort(key=lambda h: h[0])
+    for s, closed in heads:
+        idx = [s]
+        k = nxt_l[s]
+        while k != -1 and k != s:
+            idx.append(k)
+            k = nxt_l[k]
+        idx = np.asarray(idx)
+        px = np.concatenate([[sx[s]], ex[idx]])
+        py = np.concatenate([[sy[s]], ey[idx]])
+        lines.append(np.stack([px, py], axis=1))
     return lines

@@ -225,7 +225,35 @@ def gen_lcs(dl):
     save("lcs", **out)
 
 
-GROUPS = {"flows": gen_flows, "ftle_default": gen_ftle_default, "ftle_cases": gen_ftle_cases,
+def gen_contour(dl):
+    """Masked directional-derivative fields (the contour generator's input) of the
+    reference's own ridge tests: R:tests/test_diagnostics/test_lagrangian.py:20-44 (test_lcs)
+    and R:tests/test_diagnostics/test_eulerian.py:126-193 (test_iles*)."""
+    out = {}
+    x = np.linspace(0, 2, 20)
+    y = np.linspace(0, 1, 10)
+
+    def grab(obj, tag, **kw):
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                obj.compute(x, y, debug=True, **kw)
+        except RuntimeError as e:
+            assert "contourpy" in str(e)
+        dd = obj.directional_derivative
+        out[tag + "__dd"] = np.ma.filled(dd, np.nan)
+        out[tag + "__mask"] = np.ma.getmaskarray(dd)
+
+    grab(dl.diagnostics.LCS(), "lcs", f=dl.flows.double_gyre, t=(0.1, 0))
+    for kind in ("attracting", "repelling"):
+        grab(dl.diagnostics.iLES(), "iles_" + kind, f=dl.flows.double_gyre, t=0, kind=kind)
+        grab(dl.diagnostics.iLES(), "iles_raw_" + kind, f=dl.flows.double_gyre, t=0, kind=kind,
+             force_eigenvectors=False)
+    out["x"], out["y"] = x, y
+    save("contour_inputs", **out)
+
+
+GROUPS = {"contour": gen_contour, "flows": gen_flows, "ftle_default": gen_ftle_default, "ftle_cases": gen_ftle_cases,
           "eulerian": gen_eulerian, "lcs": gen_lcs, "ftle_c1": gen_ftle_c1}
 
 if __name__ == "__main__":

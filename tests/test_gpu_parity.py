@@ -324,6 +324,28 @@ def test_lcs_fields_against_reference(dl, golden, name, x, y, t, eo, pct):
         assert np.abs(np.ma.getdata(l.directional_derivative) - dd_ref)[both].max() < 1e-6 * sc
 
 
+def test_reference_ridge_tests_through_api(dl):
+    """R:tests/test_diagnostics/test_lagrangian.py:20-44 (test_lcs) and
+    R:tests/test_diagnostics/test_eulerian.py:126-193 (test_iles, test_iles_with_forced_
+    eigenvectors), verbatim inputs through the public API: same number of lines, same order,
+    same vertices.  (test_iles' expected lines are what the reference produces with
+    force_eigenvectors=False; with its default True it produces the *_forced set.)"""
+    x, y = np.linspace(0, 2, 20), np.linspace(0, 1, 10)
+    dg = dl.flows.double_gyre
+
+    def same(expected, got):
+        assert len(expected) == len(got), (len(expected), len(got))
+        assert all(a.shape == b.shape and np.isclose(a, b).all() for a, b in zip(expected, got))
+
+    same(rv.LCS_LINES, dl.diagnostics.LCS().compute(x, y, f=dg, t=(0.1, 0)))
+    iles = dl.diagnostics.iLES
+    same(rv.ILES_FORCED_ATTRACTING, iles().compute(x, y, f=dg, t=0, kind='attracting', force_eigenvectors=True))
+    same(rv.ILES_FORCED_REPELLING, iles().compute(x, y, f=dg, t=0, kind='repelling', force_eigenvectors=True))
+    same(rv.ILES_FORCED_ATTRACTING, iles().compute(x, y, f=dg, t=0, kind='attracting'))
+    same(rv.ILES_ATTRACTING, iles().compute(x, y, f=dg, t=0, kind='attracting', force_eigenvectors=False))
+    same(rv.ILES_REPELLING, iles().compute(x, y, f=dg, t=0, kind='repelling', force_eigenvectors=False))
+
+
 # ---------------------------------------------------------------- errors / edge cases
 def test_error_paths(dl):
     D, fl = dl.diagnostics, dl.flows

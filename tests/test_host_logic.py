@@ -147,23 +147,6 @@ def test_constructor_and_validation_without_gpu():
             D.FTLE().compute([0, 1, 2], [0, 1], __import__("dynlab_b200").flows.double_gyre, (2, 0))
 
 
-def test_marching_squares_simple():
-    from dynlab_b200._contour import marching_squares
-
-    x = np.linspace(-1, 1, 21)
-    y = np.linspace(-1, 1, 17)
-    X, Y = np.meshgrid(x, y)
-    lines = marching_squares(x, y, X - 0.33 * Y + 0.05)
-    assert len(lines) == 1
-    L = lines[0]
-    assert np.abs(L[:, 0] - 0.33 * L[:, 1] + 0.05).max() < 1e-12
-    z = np.ma.MaskedArray(X ** 2 + Y ** 2 - 0.5, mask=(X > 0.5))
-    lines = marching_squares(x, y, z)
-    assert len(lines) == 1 and lines[0][:, 0].max() <= 0.5 + 1e-12
-    r = np.hypot(lines[0][:, 0], lines[0][:, 1])
-    assert np.abs(r - np.sqrt(0.5)).max() < 5e-3
-
-
 # ------------------------------------------------------------------ sharding (gloo)
 def test_partition_covers_grid():
     from dynlab_b200.sharding import active_ranks, partition
