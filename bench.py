@@ -285,6 +285,16 @@ def run_ours(args):
         except OSError:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = {}
+        try:  # DRAM bytes per launch from the committed ncu --set full captures (1-GPU, config 3)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        except OSError:
+            pass
+
+        def dram(kernel):
+            t = traffic.get(kernel)
+            return (t["dram_bytes_read"] + t["dram_bytes_write"]) if (t and world == 1) else None
+
         k2_gbs = BYTES_PER_POINT_K2 * slab.rows * XDIM / (k2_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "seeds/s", "n_gpus": world,
@@ -306,15 +316,17 @@ def run_ours(args):
             "kernels_ms": {"rk45_flowmap": k1_ms, "ftle_stencil": k2_ms},
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak_flops / 1e12,
-                         "unit": "TFLOP/s", "frac": achieved / peak_flops, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak_flops,
+                         "traffic": dram("rk45_kernel"),
                          "kernel": "rk45_kernel<double_gyre> (K1)",
                          "note": "algorithmic FLOP = attempts*872 + seeds*256 (SURVEY §8d model, "
                                  "attempts counted by the kernel); peak = DFMA chain measured "
                                  "in this run (dlb_dfma_peak), theoretical 37.2 TFLOP/s at "
                                  "1965 MHz"},
             "roofline_hbm": {"bound": "hbm", "achieved": k2_gbs, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": k2_gbs / hbm_peak, "traffic": None,
-                             "kernel": "stencil_kernel<FTLE> (K2)",
+                             "frac": k2_gbs / hbm_peak,
+                             "traffic": dram("stencil_interior_kernel_ftle"),
+                             "kernel": "stencil_interior_kernel<FTLE> + stencil_edge_kernel (K2)",
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         }
         if world == 1 and not args.no_cpu:

@@ -23,7 +23,10 @@
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int RK_BLOCK = 128;
+#ifndef DLB_RK_BLOCK
+#define DLB_RK_BLOCK 128
+#endif
+constexpr int RK_BLOCK = DLB_RK_BLOCK;
 #ifndef DLB_RK_MINBLOCKS
 #define DLB_RK_MINBLOCKS 4
 #endif

@@ -1,0 +1,69 @@
+"""Time-sweep driver (BASELINE config 5): FTLE (and optionally the LCS ridge
+field) for a list of time intervals on one grid.
+
+The reference has no such entry point — its users loop over ``FTLE().compute(...)``
+(R:README.md:19-28).  Slices are independent, so they are sharded round-robin over the ranks of
+the process group with *no* data-path communication (each rank keeps whole slices; the row
+sharding of ``sharding.py`` is switched off inside the sweep); results stay on the device
+unless ``to_host`` is set.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch.distributed as dist
+
+from . import _native as nat
+from . import sharding
+from ._engine import Engine, as_coord
+from ._resolve import resolve_flow
+from .utils import ODEINT_DEFAULT_TOL, parse_integrator_kwargs
+
+
+def ftle_time_sweep(x, y, f, t_spans, edge_order: int = 1, percentile=None, ridge: bool = False,
+                    to_host: bool = True, **kwargs):
+    """FTLE fields for ``t_spans = [(t0, tf), ...]``.
+
+    Returns ``{slice_index: result}`` for the slices this rank owns (all of them without a
+    process group).  ``result`` is the FTLE field (``np.ma.MaskedArray`` or a device tensor);
+    with ``ridge=True`` it is ``(ftle, directional_derivative, ridge_mask)`` — the input of the
+    contour step of ``LCS`` (R:_base_classes.py:216-268) with ``percentile`` applied.
+    """
+    xs, ys = as_coord(np.asarray(x).squeeze()), as_coord(np.asarray(y).squeeze())
+    if xs.ndim != 1 or ys.ndim != 1:
+        raise ValueError("x and y must be 1-dimensional arrays.")
+    kw = parse_integrator_kwargs(kwargs, ODEINT_DEFAULT_TOL, ODEINT_DEFAULT_TOL)
+    _, fid, dim, params = resolve_flow(f)
+    if dim != 2:
+        raise ValueError("a 2-D diagnostic needs a 2-D flow")
+    eng = Engine.get()
+    if dist.is_available() and dist.is_initialized() and sharding._mode != "off":
+        rank, size = dist.get_rank(), dist.get_world_size()
+    else:
+        rank, size = 0, 1
+    ydim, xdim = len(ys), len(xs)
+    out = {}
+    fm = eng.empty(ydim, xdim, 2)
+    for k, span in enumerate(t_spans):
+        if k % size != rank:
+            continue
+        if len(span) != 2:
+            raise ValueError("t must only have 2 values, t_0 and t_final")
+        t0, tf = float(span[0]), float(span[1])
+        eng.flow_map(fid, params, xs, ys, 0, ydim, t0, tf, kw["rtol"], float(kw["atol"]),
+                     kw["max_step"], kw["first_step"] or 0.0, out=fm)
+        xi_mode = nat.XI_LAPACK if ridge else nat.XI_NONE
+        field, xi = eng.ftle_stencil(fm, 0, xs, ys, edge_order, abs(tf - t0), 0, ydim, xi_mode)
+        if not ridge:
+            out[k] = np.ma.MaskedArray(eng.to_host(field)) if to_host else field
+            continue
+        thr = None
+        if percentile:
+            # R:_base_classes.py:266-268 — np.percentile of the (unmasked) field values
+            thr = float(np.percentile(eng.to_host(field), percentile))
+        dd, conc, mask = eng.ridge_field(field, xi, xs, ys, edge_order, thr)
+        if to_host:
+            out[k] = (np.ma.MaskedArray(eng.to_host(field)),
+                      np.ma.MaskedArray(eng.to_host(dd), mask=eng.to_host(mask).astype(bool)))
+        else:
+            out[k] = (field, dd, mask)
+    return out

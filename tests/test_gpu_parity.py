@@ -346,6 +346,30 @@ def test_reference_ridge_tests_through_api(dl):
     same(rv.ILES_REPELLING, iles().compute(x, y, f=dg, t=0, kind='repelling', force_eigenvectors=False))
 
 
+def test_time_sweep_matches_single_calls(dl):
+    """BASELINE config 5 pattern at small size: the sweep driver returns, slice by slice, the
+    bits FTLE().compute / LCS(debug) give for the same interval."""
+    from dynlab_b200.sweep import ftle_time_sweep
+
+    x, y = np.linspace(0, 2, 65), np.linspace(0, 1, 33)
+    spans = [(k * 10 / 4 + 5.0, k * 10 / 4) for k in range(4)]
+    res = ftle_time_sweep(x, y, dl.flows.double_gyre, spans, edge_order=2, rtol=1e-8, atol=1e-8)
+    assert sorted(res) == [0, 1, 2, 3]
+    for k, span in enumerate(spans):
+        ref = dl.diagnostics.FTLE().compute(x, y, dl.flows.double_gyre, span, edge_order=2, rtol=1e-8, atol=1e-8)
+        assert np.array_equal(np.ma.getdata(res[k]), np.ma.getdata(ref))
+    res = ftle_time_sweep(x, y, dl.flows.double_gyre, spans[:2], edge_order=2, percentile=80, ridge=True,
+                          rtol=1e-8, atol=1e-8)
+    for k in (0, 1):
+        l = dl.diagnostics.LCS()
+        l.compute(x, y, f=dl.flows.double_gyre, t=spans[k], edge_order=2, percentile=80, debug=True,
+                  rtol=1e-8, atol=1e-8)
+        ftle, dd = res[k]
+        assert np.array_equal(np.ma.getdata(ftle), np.ma.getdata(l.ftle))
+        assert np.array_equal(np.ma.getmaskarray(dd), np.ma.getmaskarray(l.directional_derivative))
+        assert np.array_equal(np.ma.getdata(dd), np.ma.getdata(l.directional_derivative))
+
+
 # ---------------------------------------------------------------- errors / edge cases
 def test_error_paths(dl):
     D, fl = dl.diagnostics, dl.flows
