@@ -46,6 +46,7 @@ struct Axis {
 
 struct StencilParams {
   Axis ax, ay;
+  const double2* ay4;  // y coefficients interleaved (a, b | c, 0) per row, 32-byte records
   long long nloc, grow0;        // local slab: rows [grow0, grow0+nloc)
   long long out_row0, out_rows; // global rows to produce
   int edge_order;
@@ -200,8 +201,9 @@ __device__ __forceinline__ void edge_axis_y(const StencilParams& P, const Loader
   }
 }
 
-// Loaders: at(local_row, col) for the edge formulas; Cursor for the rolling interior walk
-// (one pointer per field, advanced by a row per iteration: no 64-bit index arithmetic in the loop).
+// Loaders: at(local_row, col) for the edge formulas; Cursor for the rolling interior walk: a
+// task-base pointer plus a 32-bit element offset (one IMAD.WIDE per access instead of 64-bit
+// pointer bumps; a task spans at most ST_ROWS + 2 rows, far below 2^31 elements).
 struct LoaderAoS {
   const double2* p;
   long long xdim;
@@ -210,8 +212,7 @@ struct LoaderAoS {
   }
   struct Cursor {
     const double2* q;
-    __device__ __forceinline__ double2 load(long long off) const { return __ldg(q + off); }
-    __device__ __forceinline__ void advance(long long n) { q += n; }
+    __device__ __forceinline__ double2 load(int off) const { return __ldg(q + off); }
   };
   __device__ __forceinline__ Cursor cursor(long long lrow, long long j) const {
     return Cursor{p + lrow * xdim + j};
@@ -229,12 +230,8 @@ struct LoaderSoA {
   struct Cursor {
     const double* qu;
     const double* qv;
-    __device__ __forceinline__ double2 load(long long off) const {
+    __device__ __forceinline__ double2 load(int off) const {
       return make_double2(__ldg(qu + off), __ldg(qv + off));
-    }
-    __device__ __forceinline__ void advance(long long n) {
-      qu += n;
-      qv += n;
     }
   };
   __device__ __forceinline__ Cursor cursor(long long lrow, long long j) const {
@@ -378,6 +375,10 @@ __device__ __forceinline__ void emit(const StencilParams& P, double2 C, double d
 // 30 columns (an ncu run of the load-based variant showed the L/R loads missing L1 43 % of the
 // time and the kernel stalled on them: long_scoreboard 7.3 per issue).
 constexpr int ST_COLS = 30;
+#ifndef DLB_ST_W
+#define DLB_ST_W 4
+#endif
+constexpr int ST_W = DLB_ST_W;  // rows held in registers: 3 in use + (ST_W - 3) prefetched
 
 __device__ __forceinline__ double2 shfl_up2(double2 v) {
   return make_double2(__shfl_up_sync(FULL, v.x, 1), __shfl_up_sync(FULL, v.y, 1));
@@ -386,8 +387,11 @@ __device__ __forceinline__ double2 shfl_down2(double2 v) {
   return make_double2(__shfl_down_sync(FULL, v.x, 1), __shfl_down_sync(FULL, v.y, 1));
 }
 
-template <int KIND, int MODE, bool XI, class Loader>
-__global__ void __launch_bounds__(ST_BLOCK, 4)
+#ifndef DLB_ST_MINB
+#define DLB_ST_MINB 4
+#endif
+template <int KIND, int MODE, bool XI, bool UX, bool UY, class Loader>
+__global__ void __launch_bounds__(ST_BLOCK, DLB_ST_MINB)
     stencil_interior_kernel(const StencilParams P, const Loader ld) {
   const long long xdim = P.ax.n, ydim = P.ay.n;
   const int lane = threadIdx.x & 31;
@@ -401,8 +405,10 @@ __global__ void __launch_bounds__(ST_BLOCK, 4)
   const long long nstrips = (ncols + ST_COLS - 1) / ST_COLS;
   const long long nchunks = (r_hi - r_lo + ST_ROWS - 1) / ST_ROWS;
   const long long ntasks = nstrips * nchunks;
-  const bool ux = P.ax.uniform != 0, uy = P.ay.uniform != 0;
   const double ix = P.ax.inv2h, iy = P.ay.inv2h;
+  const int sx = (int)xdim;  // row stride in elements
+  __shared__ double2 ysm[ST_BLOCK / 32][ST_ROWS][2];
+  const int wib = threadIdx.x >> 5;
 
   for (long long task = warp; task < ntasks; task += nwarps) {  // warp-uniform trip count
     const long long chunk = task / nstrips;
@@ -411,54 +417,73 @@ __global__ void __launch_bounds__(ST_BLOCK, 4)
     const long long j = (jj < xdim) ? jj : xdim - 1;       // clamp the loads of tail lanes
     const bool emit_lane = (lane >= 1) && (lane <= ST_COLS) && (jj <= xdim - 2);
     const long long g0 = r_lo + chunk * ST_ROWS;
-    const long long g1 = (g0 + ST_ROWS < r_hi) ? g0 + ST_ROWS : r_hi;
+    const int nrows = (int)((g0 + ST_ROWS < r_hi) ? ST_ROWS : r_hi - g0);
     double xa = 0.0, xb = 0.0, xc = 0.0;
-    if (!ux) {
+    if (!UX) {
       xa = __ldg(P.ax.ca + j);
       xb = __ldg(P.ax.cb + j);
       xc = __ldg(P.ax.cc + j);
     }
-    typename Loader::Cursor cur = ld.cursor(g0 - P.grow0, j);
-    long long o = (g0 - P.out_row0) * xdim + j;
-    // Rolling window over rows held in four registers that rotate by *renaming* (the loop is
-    // unrolled by four): the row loaded in one step is first used one step later, and no
-    // register move ever touches a load that is still in flight (a rotating `D = Dn` copy
-    // stalled on long_scoreboard for 45 % of all samples in the first ncu capture).
-    double2 r0 = cur.load(-xdim), r1 = cur.load(0), r2 = cur.load(xdim), r3 = r2;
-    long long gi = g0;
-    auto step = [&](const double2& U, const double2& C, const double2& D, double2& N) {
-      if (gi + 1 < g1) N = cur.load(2 * xdim);  // row gi+2 <= ydim-1 because gi+1 <= ydim-2
+    const typename Loader::Cursor cur = ld.cursor(g0 - P.grow0, j);
+    const long long obase = (g0 - P.out_row0) * xdim + j;
+    // y coefficients of the task's rows -> shared memory, one 32-byte record per row (lane l
+    // fetches row l).  Read straight from global they were consumed at once and, with the
+    // streaming data evicting them from L1, cost ~35 % of all stall samples (long_scoreboard).
+    if (!UY) {
+      __syncwarp();  // previous task's readers are done
+      if (lane < nrows) {
+        const double2* src = P.ay4 + 2 * (g0 + lane);
+        ysm[wib][lane][0] = __ldg(src);
+        ysm[wib][lane][1] = __ldg(src + 1);
+      }
+      __syncwarp();
+    }
+    // Rolling window over rows: ST_W registers that rotate by *renaming* (the loop is unrolled
+    // ST_W times, so every index below is static): r[s] = row k-1, r[s+1] = row k, r[s+2] =
+    // row k+1, r[s+3..] = prefetched rows; the load issued in step k is row k+ST_W-1 and is
+    // first used ST_W-3 steps later.  No register move ever touches a load that is still in
+    // flight (a rotating `D = Dn` copy stalled on long_scoreboard for 45 % of all samples in
+    // the first ncu capture).
+    double2 r[ST_W];
+#pragma unroll
+    for (int i = 0; i < ST_W; ++i) {
+      const int row = i - 1;  // relative to g0; rows up to nrows are inside the grid
+      r[i] = cur.load(((row <= nrows) ? row : nrows) * sx);
+    }
+    int k = 0;      // row within the task
+    int off = 0;    // k * sx
+    auto step = [&](int s) {  // s is a compile-time constant after unrolling
+      const double2 U = r[s % ST_W];
+      const double2 C = r[(s + 1) % ST_W], D = r[(s + 2) % ST_W];
+      if (k + ST_W - 1 <= nrows) r[s % ST_W] = cur.load(off + (ST_W - 1) * sx);
       const double2 L = shfl_up2(C), R = shfl_down2(C);
       double d0dx, d1dx, d0dy, d1dy;
-      if (ux) {
+      if (UX) {
         d0dx = (R.x - L.x) * ix;
         d1dx = (R.y - L.y) * ix;
       } else {
         d0dx = fma(xc, R.x, fma(xb, C.x, xa * L.x));
         d1dx = fma(xc, R.y, fma(xb, C.y, xa * L.y));
       }
-      if (uy) {
+      if (UY) {
         d0dy = (D.x - U.x) * iy;
         d1dy = (D.y - U.y) * iy;
       } else {
-        const double ya = __ldg(P.ay.ca + gi), yb = __ldg(P.ay.cb + gi), yc = __ldg(P.ay.cc + gi);
-        d0dy = fma(yc, D.x, fma(yb, C.x, ya * U.x));
-        d1dy = fma(yc, D.y, fma(yb, C.y, ya * U.y));
+        const double2 yab = ysm[wib][k][0], ycz = ysm[wib][k][1];
+        d0dy = fma(ycz.x, D.x, fma(yab.y, C.x, yab.x * U.x));
+        d1dy = fma(ycz.x, D.y, fma(yab.y, C.y, yab.x * U.y));
       }
-      if (emit_lane) emit<KIND, MODE, XI>(P, C, d0dx, d1dx, d0dy, d1dy, o);
-      cur.advance(xdim);
-      o += xdim;
-      ++gi;
+      if (emit_lane) emit<KIND, MODE, XI>(P, C, d0dx, d1dx, d0dy, d1dy, obase + off);
+      off += sx;
+      ++k;
     };
-    while (gi + 4 <= g1) {
-      step(r0, r1, r2, r3);
-      step(r1, r2, r3, r0);
-      step(r2, r3, r0, r1);
-      step(r3, r0, r1, r2);
+    while (k + ST_W <= nrows) {
+#pragma unroll
+      for (int s = 0; s < ST_W; ++s) step(s);
     }
-    if (gi < g1) step(r0, r1, r2, r3);
-    if (gi < g1) step(r1, r2, r3, r0);
-    if (gi < g1) step(r2, r3, r0, r1);
+#pragma unroll
+    for (int s = 0; s < ST_W - 1; ++s)
+      if (k < nrows) step(s);
   }
 }
 
@@ -521,8 +546,15 @@ int launch_stencil(const StencilParams& P, const Loader& ld, cudaStream_t stream
     const long long nchunks = (r_hi - r_lo + ST_ROWS - 1) / ST_ROWS;
     long long blocks = (nstrips * nchunks + ST_BLOCK / 32 - 1) / (ST_BLOCK / 32);
     if (blocks > cap) blocks = cap;
-    stencil_interior_kernel<KIND, MODE, XI, Loader>
-        <<<(unsigned)blocks, ST_BLOCK, 0, stream>>>(P, ld);
+    const unsigned g = (unsigned)blocks;
+    if (P.ax.uniform && P.ay.uniform)
+      stencil_interior_kernel<KIND, MODE, XI, true, true, Loader><<<g, ST_BLOCK, 0, stream>>>(P, ld);
+    else if (P.ax.uniform)
+      stencil_interior_kernel<KIND, MODE, XI, true, false, Loader><<<g, ST_BLOCK, 0, stream>>>(P, ld);
+    else if (P.ay.uniform)
+      stencil_interior_kernel<KIND, MODE, XI, false, true, Loader><<<g, ST_BLOCK, 0, stream>>>(P, ld);
+    else
+      stencil_interior_kernel<KIND, MODE, XI, false, false, Loader><<<g, ST_BLOCK, 0, stream>>>(P, ld);
     DLB_CUDA_CHECK(cudaGetLastError());
   }
   return DLB_OK;
@@ -690,13 +722,20 @@ int setup_axes(StencilParams& P, const double* h_x, int64_t xdim, const double* 
     build_axis(h_x, xdim, edge_order, &cache.hx);
     build_axis(h_y, ydim, edge_order, &cache.hy);
     const HostAxis &hx = cache.hx, &hy = cache.hy;
-    std::vector<double> stage(3 * (xdim + ydim));
+    std::vector<double> stage(3 * (xdim + ydim) + 4 * ydim);
     memcpy(&stage[0], hx.ca.data(), sizeof(double) * xdim);
     memcpy(&stage[xdim], hx.cb.data(), sizeof(double) * xdim);
     memcpy(&stage[2 * xdim], hx.cc.data(), sizeof(double) * xdim);
     memcpy(&stage[3 * xdim], hy.ca.data(), sizeof(double) * ydim);
     memcpy(&stage[3 * xdim + ydim], hy.cb.data(), sizeof(double) * ydim);
     memcpy(&stage[3 * xdim + 2 * ydim], hy.cc.data(), sizeof(double) * ydim);
+    double* y4 = &stage[3 * (xdim + ydim)];
+    for (int64_t i = 0; i < ydim; ++i) {
+      y4[4 * i] = hy.ca[i];
+      y4[4 * i + 1] = hy.cb[i];
+      y4[4 * i + 2] = hy.cc[i];
+      y4[4 * i + 3] = 0.0;
+    }
     // pageable source: cudaMemcpyAsync stages it before returning, so `stage` may die here
     DLB_CUDA_CHECK(cudaMemcpyAsync(base, stage.data(), sizeof(double) * stage.size(),
                                    cudaMemcpyHostToDevice, stream));
@@ -714,6 +753,7 @@ int setup_axes(StencilParams& P, const double* h_x, int64_t xdim, const double* 
   const HostAxis &hx = cache.hx, &hy = cache.hy;
   P.ax = Axis{dxa, dxa + xdim, dxa + 2 * xdim, xdim, hx.inv2h, hx.w_first, hx.w_last, hx.uniform};
   P.ay = Axis{dya, dya + ydim, dya + 2 * ydim, ydim, hy.inv2h, hy.w_first, hy.w_last, hy.uniform};
+  P.ay4 = (const double2*)(base + 3 * (xdim + ydim));  // 32-byte aligned: 256 + 32 (xdim+ydim)
   P.edge_order = edge_order;
   return DLB_OK;
 }
