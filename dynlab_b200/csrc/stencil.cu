@@ -22,6 +22,7 @@
 #include <math_constants.h>
 
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -210,6 +211,7 @@ struct LoaderAoS {
   __device__ __forceinline__ double2 at(long long lrow, long long j) const {
     return __ldg(p + lrow * xdim + j);
   }
+  bool aligned16() const { return ((uintptr_t)p & 15u) == 0; }
   struct Cursor {
     const double2* q;
     __device__ __forceinline__ double2 load(int off) const { return __ldg(q + off); }
@@ -227,6 +229,7 @@ struct LoaderSoA {
     const long long k = lrow * xdim + j;
     return make_double2(__ldg(u + k), __ldg(v + k));
   }
+  bool aligned16() const { return (((uintptr_t)u | (uintptr_t)v) & 15u) == 0; }
   struct Cursor {
     const double* qu;
     const double* qv;
@@ -295,6 +298,11 @@ __device__ __forceinline__ double fast_log_ge1(double x) {
   const double hi_part = fma(ed, ST_LOGK[9], 2.0 * sq);
   const double lo_part = fma(ed, ST_LOGK[10], sq * z * p);
   return hi_part + lo_part;
+}
+
+int env_flag(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
 }
 
 int g_sms = 0;
@@ -487,6 +495,191 @@ __global__ void __launch_bounds__(ST_BLOCK, DLB_ST_MINB)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bulk-copy (TMA engine) variant of the interior kernel.  The register-window kernel above is
+// latency-bound (ncu: long_scoreboard dominates, DRAM ~55 %): a warp can only keep as many row
+// segments in flight as it has registers for.  Here one elected thread per CTA streams row
+// segments into a shared-memory ring with `cp.async.bulk` (SASS: UBLKCP) completing on
+// mbarriers, so the bytes in flight (TB_SLOTS - 2 rows x 2 KB per CTA, 8 CTAs per SM) no longer
+// depend on registers; the 128 threads of the CTA (one per loaded column, the two outermost
+// are halo-only) read neighbours straight from shared memory.
+// Requirements: 16-byte aligned row segments — always true for the AoS flow map, true for the
+// SoA velocity fields when xdim is even (otherwise the register-window kernel is used).
+constexpr int TB_THREADS = 128;          // loaded columns per row segment = threads per CTA
+constexpr int TB_OUT = TB_THREADS - 2;   // output columns per CTA strip
+#ifndef DLB_TB_SLOTS
+#define DLB_TB_SLOTS 8
+#endif
+#ifndef DLB_TB_ROWS
+#define DLB_TB_ROWS 64
+#endif
+constexpr int TB_SLOTS = DLB_TB_SLOTS;    // rows in the shared-memory ring
+constexpr int TB_ROWS = DLB_TB_ROWS;      // output rows per task
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
+                                         unsigned long long* b) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(b))
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* b, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// ring row = 2048 bytes: AoS 128 x double2, SoA 128 x u then 128 x v
+struct RingAoS {
+  static __device__ __forceinline__ void issue(const LoaderAoS& ld, double* slot, long long lrow,
+                                               long long c0, int ncol, unsigned long long* bar) {
+    mbar_expect_tx(bar, (unsigned)ncol * 16u);
+    bulk_g2s(slot, ld.p + lrow * ld.xdim + c0, (unsigned)ncol * 16u, bar);
+  }
+  static __device__ __forceinline__ double2 read(const double* slot, int t) {
+    return reinterpret_cast<const double2*>(slot)[t];
+  }
+};
+struct RingSoA {
+  static __device__ __forceinline__ void issue(const LoaderSoA& ld, double* slot, long long lrow,
+                                               long long c0, int ncol, unsigned long long* bar) {
+    mbar_expect_tx(bar, (unsigned)ncol * 16u);
+    const long long k = lrow * ld.xdim + c0;
+    bulk_g2s(slot, ld.u + k, (unsigned)ncol * 8u, bar);
+    bulk_g2s(slot + TB_THREADS, ld.v + k, (unsigned)ncol * 8u, bar);
+  }
+  static __device__ __forceinline__ double2 read(const double* slot, int t) {
+    return make_double2(slot[t], slot[TB_THREADS + t]);
+  }
+};
+
+template <int KIND, int MODE, bool XI, bool UX, bool UY, class Loader, class Ring>
+__global__ void __launch_bounds__(TB_THREADS, 8)
+    stencil_bulk_kernel(const StencilParams P, const Loader ld) {
+  __shared__ __align__(128) double ring[TB_SLOTS][2 * TB_THREADS];
+  __shared__ __align__(8) unsigned long long full[TB_SLOTS];
+  __shared__ double2 ysm[TB_ROWS][2];
+  const long long xdim = P.ax.n, ydim = P.ay.n;
+  const int t = threadIdx.x;
+  const long long r_lo = (P.out_row0 > 1) ? P.out_row0 : 1;
+  const long long r_hi = (P.out_row0 + P.out_rows < ydim - 1) ? P.out_row0 + P.out_rows : ydim - 1;
+  const long long ncols_out = xdim - 2;
+  if (r_hi <= r_lo || ncols_out <= 0) return;
+  const long long nstrips = (ncols_out + TB_OUT - 1) / TB_OUT;
+  const long long nchunks = (r_hi - r_lo + TB_ROWS - 1) / TB_ROWS;
+  const long long ntasks = nstrips * nchunks;
+  const double ix = P.ax.inv2h, iy = P.ay.inv2h;
+  if (t == 0) {
+#pragma unroll
+    for (int i = 0; i < TB_SLOTS; ++i) mbar_init(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned nbase = 0;  // rows that went through the ring before this task (CTA-uniform)
+
+  for (long long task = blockIdx.x; task < ntasks; task += gridDim.x) {
+    const long long chunk = task / nstrips;
+    const long long strip = task - chunk * nstrips;
+    const long long c0 = strip * TB_OUT;  // first loaded column (even)
+    const int ncol = (int)((c0 + TB_THREADS <= xdim) ? TB_THREADS : xdim - c0);
+    const long long g0 = r_lo + chunk * TB_ROWS;
+    const int nrows = (int)((g0 + TB_ROWS < r_hi) ? TB_ROWS : r_hi - g0);
+    const int nload = nrows + 2;             // rows g0-1 .. g0+nrows
+    const long long lrow0 = g0 - 1 - P.grow0;  // local row of the first loaded row
+    const int tc = (t < ncol) ? t : ncol - 1;  // clamped column of this thread inside the segment
+    const long long col = c0 + tc;
+    const bool emit_thread = (t >= 1) && (t <= TB_OUT) && (c0 + t <= xdim - 2);
+
+    __syncthreads();  // the previous task's ring and ysm are no longer read
+    if (t == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const int first = (nload < TB_SLOTS) ? nload : TB_SLOTS;
+      for (int i = 0; i < first; ++i)
+        Ring::issue(ld, ring[(nbase + i) % TB_SLOTS], lrow0 + i, c0, ncol, &full[(nbase + i) % TB_SLOTS]);
+    }
+    if (!UY && t < nrows) {
+      const double2* src = P.ay4 + 2 * (g0 + t);
+      ysm[t][0] = __ldg(src);
+      ysm[t][1] = __ldg(src + 1);
+    }
+    double xa = 0.0, xb = 0.0, xc = 0.0;
+    if (!UX) {
+      xa = __ldg(P.ax.ca + col);
+      xb = __ldg(P.ax.cb + col);
+      xc = __ldg(P.ax.cc + col);
+    }
+    __syncthreads();  // ysm visible
+
+    auto wait_row = [&](int i) {  // loaded row i of this task has landed
+      const unsigned n = nbase + (unsigned)i;
+      unsigned long long* b = &full[n % TB_SLOTS];
+      const unsigned parity = (n / TB_SLOTS) & 1u;
+      while (!mbar_try_wait(b, parity)) {
+      }
+      return ring[n % TB_SLOTS];
+    };
+    double2 U = Ring::read(wait_row(0), tc);
+    const double* slotC = wait_row(1);
+    double2 C = Ring::read(slotC, tc);
+    long long o = (g0 - P.out_row0) * xdim + col;
+    for (int k = 0; k < nrows; ++k) {
+      const double* slotD = wait_row(k + 2);
+      const double2 D = Ring::read(slotD, tc);
+      const double2 L = Ring::read(slotC, (tc > 0) ? tc - 1 : 0);
+      const double2 R = Ring::read(slotC, (tc < ncol - 1) ? tc + 1 : ncol - 1);
+      double d0dx, d1dx, d0dy, d1dy;
+      if (UX) {
+        d0dx = (R.x - L.x) * ix;
+        d1dx = (R.y - L.y) * ix;
+      } else {
+        d0dx = fma(xc, R.x, fma(xb, C.x, xa * L.x));
+        d1dx = fma(xc, R.y, fma(xb, C.y, xa * L.y));
+      }
+      if (UY) {
+        d0dy = (D.x - U.x) * iy;
+        d1dy = (D.y - U.y) * iy;
+      } else {
+        const double2 yab = ysm[k][0], ycz = ysm[k][1];
+        d0dy = fma(ycz.x, D.x, fma(yab.y, C.x, yab.x * U.x));
+        d1dy = fma(ycz.x, D.y, fma(yab.y, C.y, yab.x * U.y));
+      }
+      if (emit_thread) emit<KIND, MODE, XI>(P, C, d0dx, d1dx, d0dy, d1dy, o);
+      o += xdim;
+      U = C;
+      C = D;
+      slotC = slotD;
+      // Loaded rows <= k+1 are dead in shared memory once every thread has passed this point
+      // (row k+2 is still read as the x-neighbour row of the next iteration): refill the slot
+      // of row k with row k+TB_SLOTS, i.e. the ring runs TB_SLOTS-3 rows ahead of the compute.
+      __syncthreads();
+      if (t == 0 && k + TB_SLOTS < nload) {
+        const unsigned n = nbase + (unsigned)(k + TB_SLOTS);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        Ring::issue(ld, ring[n % TB_SLOTS], lrow0 + k + TB_SLOTS, c0, ncol, &full[n % TB_SLOTS]);
+      }
+    }
+    nbase += (unsigned)nload;
+  }
+}
+
 // Edge kernel: the O(xdim + ydim) output nodes on the grid boundary (global rows 0 and
 // ydim-1 in full, columns 0 and xdim-1 of the other rows) with numpy's one-sided formulas.
 template <int KIND, int MODE, bool XI, class Loader>
@@ -542,6 +735,27 @@ int launch_stencil(const StencilParams& P, const Loader& ld, cudaStream_t stream
   // interior
   const long long r_lo = (r0 > 1) ? r0 : 1, r_hi = (r1 < ydim - 1) ? r1 : ydim - 1;
   if (r_hi > r_lo && xdim > 2) {
+    constexpr bool aos = std::is_same<Loader, LoaderAoS>::value;
+    using Ring = typename std::conditional<aos, RingAoS, RingSoA>::type;
+    const bool bulk_ok = !XI && env_flag("DLB_STENCIL_BULK", 1) && (aos || (xdim % 2 == 0)) &&
+                         ld.aligned16();
+    if (bulk_ok) {
+      const long long nstrips = (xdim - 2 + TB_OUT - 1) / TB_OUT;
+      const long long nchunks = (r_hi - r_lo + TB_ROWS - 1) / TB_ROWS;
+      long long blocks = nstrips * nchunks;
+      if (blocks > cap) blocks = cap;
+      const unsigned g = (unsigned)blocks;
+      if (P.ax.uniform && P.ay.uniform)
+        stencil_bulk_kernel<KIND, MODE, false, true, true, Loader, Ring><<<g, TB_THREADS, 0, stream>>>(P, ld);
+      else if (P.ax.uniform)
+        stencil_bulk_kernel<KIND, MODE, false, true, false, Loader, Ring><<<g, TB_THREADS, 0, stream>>>(P, ld);
+      else if (P.ay.uniform)
+        stencil_bulk_kernel<KIND, MODE, false, false, true, Loader, Ring><<<g, TB_THREADS, 0, stream>>>(P, ld);
+      else
+        stencil_bulk_kernel<KIND, MODE, false, false, false, Loader, Ring><<<g, TB_THREADS, 0, stream>>>(P, ld);
+      DLB_CUDA_CHECK(cudaGetLastError());
+      return DLB_OK;
+    }
     const long long nstrips = (xdim - 2 + ST_COLS - 1) / ST_COLS;
     const long long nchunks = (r_hi - r_lo + ST_ROWS - 1) / ST_ROWS;
     long long blocks = (nstrips * nchunks + ST_BLOCK / 32 - 1) / (ST_BLOCK / 32);
