@@ -370,6 +370,45 @@ def test_time_sweep_matches_single_calls(dl):
         assert np.array_equal(np.ma.getdata(dd), np.ma.getdata(l.directional_derivative))
 
 
+def test_no_out_of_bounds_writes(dl):
+    """compute-sanitizer is closed on this pool, so bounds are checked by hand: outputs are
+    carved out of a larger buffer whose guard bands (canary values before and after) must
+    survive every kernel, over odd / even / tiny shapes and both interior-kernel variants."""
+    import os
+
+    from dynlab_b200._engine import Engine
+    from dynlab_b200._resolve import resolve_flow
+
+    eng = Engine.get()
+    _, fid, _, params = resolve_flow(dl.flows.double_gyre)
+    guard = 4096
+    canary = -7.25e300
+    try:
+        for bulk in ("1", "0"):
+            os.environ["DLB_STENCIL_BULK"] = bulk
+            for (nx, ny, eo) in ((2, 2, 1), (3, 3, 2), (127, 5, 2), (128, 66, 1), (129, 67, 2), (257, 131, 2), (1000, 3, 2)):
+                x, y = np.linspace(0, 2, nx), np.linspace(0, 1, ny)
+                big = torch.full((guard + ny * nx * 2 + guard,), canary, dtype=torch.float64, device=eng.device)
+                fm = big[guard:guard + ny * nx * 2].view(ny, nx, 2)
+                eng.flow_map(fid, params, x, y, 0, ny, 2.0, 0.0, 1e-6, 1e-6, out=fm)
+                bigf = torch.full((guard + ny * nx + guard,), canary, dtype=torch.float64, device=eng.device)
+                fo = bigf[guard:guard + ny * nx].view(ny, nx)
+                eng.ftle_stencil(fm, 0, x, y, eo, 2.0, 0, ny, out=fo)
+                torch.cuda.synchronize()
+                for b, n in ((big, ny * nx * 2), (bigf, ny * nx)):
+                    assert (b[:guard] == canary).all() and (b[guard + n:] == canary).all(), (bulk, nx, ny, eo)
+                    assert not (b[guard:guard + n] == canary).any(), (bulk, nx, ny, eo)  # every element written
+                # row-slab call: only the requested rows are written
+                if ny >= 6:
+                    bigf.fill_(canary)
+                    eng.ftle_stencil(fm[1:ny - 1], 1, x, y, eo, 2.0, 2, ny - 4, out=fo[2:ny - 2])
+                    torch.cuda.synchronize()
+                    assert (fo[:2] == canary).all() and (fo[ny - 2:] == canary).all()
+                    assert not (fo[2:ny - 2] == canary).any()
+    finally:
+        os.environ.pop("DLB_STENCIL_BULK", None)
+
+
 # ---------------------------------------------------------------- errors / edge cases
 def test_error_paths(dl):
     D, fl = dl.diagnostics, dl.flows
