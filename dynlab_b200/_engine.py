@@ -49,6 +49,7 @@ class Engine:
         self.device = torch.device("cuda", index)
         self._workspace = None
         self.counters = torch.zeros(nat.CNT_WORDS, dtype=torch.int64, device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)  # D2H overlapped with compute
         self.profile = None  # set to {} to collect (start, end) CUDA events per kernel name
         self.launches = 0    # kernels of libdynlab_b200.so launched through this engine
 
@@ -100,15 +101,17 @@ class Engine:
         torch.cuda.current_stream(self.device).synchronize()
         return h.numpy()
 
-    def read_counters(self) -> dict:
-        c = self.counters.cpu().numpy()
+    def read_counters(self, tensors=None) -> dict:
+        """Integrator counters of the last K1 launch, or summed over ``tensors`` ([n, 8])."""
+        c = self.counters.cpu().numpy() if tensors is None else tensors.sum(dim=0).cpu().numpy()
         return {"nfev": int(c[nat.CNT_NFEV]), "accepted": int(c[nat.CNT_ACCEPTED]),
                 "rejected": int(c[nat.CNT_REJECTED]), "failed": int(c[nat.CNT_FAILED]),
                 "seeds": int(c[nat.CNT_SEEDS])}
 
     # -- K1 ---------------------------------------------------------------------------
     def flow_map(self, flow_id, params, x, y, row0, rows, t0, tf, rtol, atol,
-                 max_step=math.inf, first_step=0.0, out=None, nfev=None, status=None):
+                 max_step=math.inf, first_step=0.0, out=None, nfev=None, status=None,
+                 counters=None):
         """Enqueue K1 for rows [row0, row0+rows) of the grid; returns the [rows, xdim, 2] tensor."""
         xdim = len(x)
         with torch.cuda.device(self.device):
@@ -122,7 +125,8 @@ class Engine:
                 float(t0), float(tf), float(rtol), float(atol), float(max_step), float(first_step),
                 out.data_ptr(), nfev.data_ptr() if nfev is not None else None,
                 status.data_ptr() if status is not None else None,
-                self.counters.data_ptr(), ws, wsz, self.stream()))
+                (self.counters if counters is None else counters).data_ptr(), ws, wsz,
+                self.stream()))
         return out
 
     def rk45_endpoints(self, flow_id, params, seeds, t0, tf, rtol, atol, max_step=math.inf,

@@ -185,12 +185,10 @@ class LagrangianDiagnostic2D(Diagnostic2D, ABC):
             f"dynlab_b200.utils.odeint_wrapper (default) or rk45_wrapper; there is no CPU "
             f"fallback for Python integrators")
 
-    @abstractmethod
-    def compute(self, x, y, f, t, **kwargs):
-        """Integrate this rank's row slab.  Returns ``(local, slab)`` where ``local`` is the
-        device tensor ``[slab.nloc, xdim, 2]`` with the own rows filled and the halo rows
-        exchanged; attribute ``flow_map`` (host ``[ydim, xdim, 2]``) is materialised lazily."""
-        super().compute(x, y)
+    def _plan(self, x, y, f, t, kwargs) -> dict:
+        """Validate the arguments exactly like the reference / scipy would and resolve the flow
+        and the integrator options into what K1 needs."""
+        Diagnostic2D.compute(self, x, y)
         if len(t) != 2:
             raise ValueError("t must only have 2 values, t_0 and t_final")
         kw = self._tolerances(kwargs)
@@ -214,16 +212,31 @@ class LagrangianDiagnostic2D(Diagnostic2D, ABC):
         if kw["rtol"] < 100 * np.finfo(float).eps:
             warnings.warn("At least one element of `rtol` is too small. "
                           f"Setting `rtol = np.maximum(rtol, {100 * np.finfo(float).eps})`.")
+        return dict(fid=fid, params=params, t0=t0, tf=tf, rtol=kw["rtol"], atol=float(atol),
+                    max_step=kw["max_step"], first_step=first or 0.0)
 
+    def _integrate_rows(self, plan, row0, rows, out, counters=None):
+        """Enqueue K1 for rows [row0, row0 + rows) of the grid into ``out`` ([rows, xdim, 2])."""
+        return Engine.get().flow_map(plan["fid"], plan["params"], self._xf, self._yf, row0, rows,
+                                     plan["t0"], plan["tf"], plan["rtol"], plan["atol"],
+                                     plan["max_step"], plan["first_step"], out=out,
+                                     counters=counters)
+
+    @abstractmethod
+    def compute(self, x, y, f, t, **kwargs):
+        """Integrate this rank's row slab.  Returns ``(local, slab)`` where ``local`` is the
+        device tensor ``[slab.nloc, xdim, 2]`` with the own rows filled and the halo rows
+        exchanged; attribute ``flow_map`` (host ``[ydim, xdim, 2]``) is materialised lazily."""
+        plan = self._plan(x, y, f, t, kwargs)
         eng = Engine.get()
         rank, size = sharding.world()
         slab = sharding.partition(self.ydim, size, rank)
         local = eng.empty(max(slab.nloc, 1), self.xdim, 2)
         if slab.rows:
             own = local[slab.halo_lo:slab.halo_lo + slab.rows]
-            eng.flow_map(fid, params, self._xf, self._yf, slab.row0, slab.rows, t0, tf,
-                         kw["rtol"], float(atol), kw["max_step"], first or 0.0, out=own)
+            self._integrate_rows(plan, slab.row0, slab.rows, own)
         self._counters_pending = slab.rows > 0
+        self._counter_tensors = None
         own = local[slab.halo_lo:slab.halo_lo + slab.rows]
         if size > 1:
             sharding.exchange_halo(local, slab, self.ydim, rank, size)
@@ -246,7 +259,7 @@ class LagrangianDiagnostic2D(Diagnostic2D, ABC):
         seeds scipy would have ended with status -1; the reference keeps their last state
         silently (R:_base_classes.py:180-182), so the values are kept."""
         if getattr(self, "_counters_pending", False):
-            self.stats = Engine.get().read_counters()
+            self.stats = Engine.get().read_counters(getattr(self, "_counter_tensors", None))
             self._counters_pending = False
             if self.stats["failed"]:
                 warnings.warn(f"{self.stats['failed']} trajectories stopped early: required step "

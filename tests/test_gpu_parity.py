@@ -346,6 +346,23 @@ def test_reference_ridge_tests_through_api(dl):
     same(rv.ILES_REPELLING, iles().compute(x, y, f=dg, t=0, kind='repelling', force_eigenvectors=False))
 
 
+def test_pipelined_compute_is_bit_identical(dl):
+    """FTLE.compute on large single-GPU grids integrates in row chunks and overlaps the
+    device-to-host copy; field, flow map and counters equal the one-shot path bit for bit."""
+    x, y = np.linspace(0, 2, 2048), np.linspace(0, 1, 2051)
+    a = dl.diagnostics.FTLE()
+    assert a.pipeline_chunks > 1
+    fa = a.compute(x, y, dl.flows.double_gyre, (1.5, 0), edge_order=2, rtol=1e-6, atol=1e-6)
+    b = dl.diagnostics.FTLE()
+    b.pipeline_chunks = 1
+    fb = b.compute(x, y, dl.flows.double_gyre, (1.5, 0), edge_order=2, rtol=1e-6, atol=1e-6)
+    assert np.array_equal(np.ma.getdata(fa), np.ma.getdata(fb))
+    assert np.array_equal(a.flow_map, b.flow_map)
+    assert a.stats == b.stats and a.stats["seeds"] == 2048 * 2051
+    c = dl.diagnostics.FTLE().compute_device(x, y, dl.flows.double_gyre, (1.5, 0), edge_order=2, rtol=1e-6, atol=1e-6)
+    assert np.array_equal(c.cpu().numpy(), np.ma.getdata(fb))
+
+
 def test_time_sweep_matches_single_calls(dl):
     """BASELINE config 5 pattern at small size: the sweep driver returns, slice by slice, the
     bits FTLE().compute / LCS(debug) give for the same interval."""
