@@ -298,6 +298,10 @@ def test_eulerian_function_route_matches_velocity_route(dl):
     gs = np.abs(u).max() / np.diff(x).min()
     assert np.abs(a - b).max() < 1e-12 * gs
     assert np.abs(d.u - u).max() < 1e-11 * np.abs(u).max()  # lazily downloaded K0 output
+    # CUDA tensors in, CUDA tensor out: nothing crosses PCIe
+    ud, vd = torch.tensor(u, device="cuda"), torch.tensor(v, device="cuda")
+    c = D.AttractionRate().compute_device(x, y, u=ud, v=vd, edge_order=2)
+    assert c.is_cuda and np.array_equal(c.cpu().numpy(), np.ma.getdata(a))
 
 
 @pytest.mark.parametrize("name,x,y,t,eo,pct", [

@@ -147,6 +147,20 @@ def test_constructor_and_validation_without_gpu():
             D.FTLE().compute([0, 1, 2], [0, 1], __import__("dynlab_b200").flows.double_gyre, (2, 0))
 
 
+def test_install_as_dynlab():
+    import subprocess
+    import sys
+
+    code = ("import dynlab_b200; dynlab_b200.install_as_dynlab();"
+            "from dynlab.diagnostics import FTLE, LCS, AttractionRate, RepulsionRate, iLES, "
+            "TrajectoryRepulsionRate, TrajectoryRepulsionRatio;"
+            "from dynlab.flows import double_gyre, lorenz; from dynlab.utils import odeint_wrapper, "
+            "force_eigenvectors2D; import dynlab; print(dynlab.__name__, FTLE.__module__)")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0, out.stderr
+    assert "dynlab_b200 dynlab_b200.diagnostics.lagrangian" in out.stdout
+
+
 # ------------------------------------------------------------------ sharding (gloo)
 def test_partition_covers_grid():
     from dynlab_b200.sharding import active_ranks, partition
