@@ -23,6 +23,9 @@ def _ftle_on_device(diag, local, slab, t, edge_order, xi_mode):
     if edge_order > 2:
         raise ValueError("'edge_order' greater than 2 not supported")
     t_span = abs(float(t[-1]) - float(t[0]))
+    if t_span == 0.0:
+        # the reference evaluates 1.0 / (2.0 * abs(t[-1] - t[0])) in Python (R:lagrangian.py:71)
+        raise ZeroDivisionError("float division by zero")
     if size == 1:
         return eng.ftle_stencil(local, 0, diag._xf, diag._yf, edge_order, t_span, 0, diag.ydim,
                                 xi_mode)
@@ -76,6 +79,8 @@ class FTLE(LagrangianDiagnostic2D):
         host = torch.empty((ydim, xdim), dtype=torch.float64, pin_memory=True)
         counters = torch.zeros(n, nat.CNT_WORDS, dtype=torch.int64, device=eng.device)
         t_span = abs(float(t[-1]) - float(t[0]))
+        if t_span == 0.0:
+            raise ZeroDivisionError("float division by zero")  # R:lagrangian.py:71
         main = torch.cuda.current_stream(eng.device)
         done = 0  # FTLE rows already produced
         for c in range(n):

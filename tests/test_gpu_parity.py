@@ -450,6 +450,8 @@ def test_error_paths(dl):
         D.FTLE(integrator=lambda f, t, Y: None).compute(x, y, fl.double_gyre, (0, 1))
     with pytest.raises(TypeError):
         D.FTLE().compute(x, y, fl.double_gyre, (0, 1), hmax=0.1)
+    with pytest.raises(ZeroDivisionError):  # T == 0: the reference divides by 2|T| in Python
+        D.FTLE().compute(x, y, fl.double_gyre, (1.0, 1.0))
     with pytest.raises(RuntimeError):
         D.AttractionRate().compute(x, y)
     with pytest.raises(ValueError):
