@@ -103,7 +103,7 @@ class Engine:
 
     def read_counters(self, tensors=None) -> dict:
         """Integrator counters of the last K1 launch, or summed over ``tensors`` ([n, 8])."""
-        c = self.counters.cpu().numpy() if tensors is None else tensors.sum(dim=0).cpu().numpy()
+        c = self.counters.cpu().numpy() if tensors is None else tensors.cpu().numpy().sum(axis=0)
         return {"nfev": int(c[nat.CNT_NFEV]), "accepted": int(c[nat.CNT_ACCEPTED]),
                 "rejected": int(c[nat.CNT_REJECTED]), "failed": int(c[nat.CNT_FAILED]),
                 "seeds": int(c[nat.CNT_SEEDS])}

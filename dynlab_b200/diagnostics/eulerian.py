@@ -17,14 +17,11 @@ class _AttractionRepulsionRate(EulerianDiagnostic2D):
 
     def compute(self, x, y, u=None, v=None, f=None, t=None, edge_order: int = 1,
                 eigenvalue_index: int = 0):
-        field = self.compute_device(x, y, u, v, f, t, edge_order, eigenvalue_index)
+        field = self._eigen_field_device(x, y, u, v, f, t, edge_order, eigenvalue_index)
         return np.ma.MaskedArray(Engine.get().to_host(field))
 
-    def compute_device(self, x, y, u=None, v=None, f=None, t=None, edge_order: int = 1,
-                       eigenvalue_index: int = 0):
-        """Same computation with the result left on the device (``torch.Tensor[ydim, xdim]``);
-        ``u, v`` may be CUDA tensors, in which case nothing crosses PCIe."""
-        ud, vd = super().compute(x, y, u, v, f, t, edge_order)
+    def _eigen_field_device(self, x, y, u, v, f, t, edge_order, eigenvalue_index):
+        ud, vd = EulerianDiagnostic2D.compute(self, x, y, u, v, f, t, edge_order)
         if eigenvalue_index not in (0, -1, 1, -2):
             raise IndexError(f"index {eigenvalue_index} is out of bounds for axis 0 with size 2")
         mode = nat.EULER_S_MIN if eigenvalue_index in (0, -2) else nat.EULER_S_MAX
@@ -41,7 +38,9 @@ class AttractionRate(_AttractionRepulsionRate):
         return self.field
 
     def compute_device(self, x, y, u=None, v=None, f=None, t=None, edge_order: int = 1):
-        return super().compute_device(x, y, u, v, f, t, edge_order, 0)
+        """Same computation with the result left on the device (``torch.Tensor[ydim, xdim]``);
+        ``u, v`` may be CUDA tensors, in which case nothing crosses PCIe."""
+        return self._eigen_field_device(x, y, u, v, f, t, edge_order, 0)
 
 
 class RepulsionRate(_AttractionRepulsionRate):
@@ -52,7 +51,8 @@ class RepulsionRate(_AttractionRepulsionRate):
         return self.field
 
     def compute_device(self, x, y, u=None, v=None, f=None, t=None, edge_order: int = 1):
-        return super().compute_device(x, y, u, v, f, t, edge_order, -1)
+        """Device-resident variant, see ``AttractionRate.compute_device``."""
+        return self._eigen_field_device(x, y, u, v, f, t, edge_order, -1)
 
 
 class _TrajectoryRepulsionRateRatio(EulerianDiagnostic2D):
