@@ -73,7 +73,9 @@ class FTLE(LagrangianDiagnostic2D):
             raise ValueError("'edge_order' greater than 2 not supported")
         eng = Engine.get()
         n, ydim, xdim = self.pipeline_chunks, self.ydim, self.xdim
-        bounds = [ydim * c // n for c in range(n + 1)]
+        # equal chunks except a short last one: only its device-to-host copy is left exposed
+        last = max(64, ydim // (4 * n))
+        bounds = [(ydim - last) * c // (n - 1) for c in range(n)] + [ydim]
         fm = eng.empty(ydim, xdim, 2)
         field = eng.empty(ydim, xdim)
         host = torch.empty((ydim, xdim), dtype=torch.float64, pin_memory=True)
