@@ -147,6 +147,18 @@ def test_constructor_and_validation_without_gpu():
             D.FTLE().compute([0, 1, 2], [0, 1], __import__("dynlab_b200").flows.double_gyre, (2, 0))
 
 
+def test_missing_native_library_fails_loudly():
+    """No CPU fallback: without the CUDA extension the package refuses to import its diagnostics."""
+    import subprocess
+    import sys
+
+    code = "import dynlab_b200.diagnostics"
+    env = dict(os.environ, DLB_LIB_PATH="/nonexistent/libdynlab_b200.so")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, env=env)
+    assert out.returncode != 0
+    assert "NativeLibraryMissing" in out.stderr and "no CPU fallback" in out.stderr
+
+
 def test_install_as_dynlab():
     import subprocess
     import sys
