@@ -550,6 +550,74 @@ def test_ftle_c3_full_size_properties(dl):
     assert (back - seeds).abs().max().item() < 1e-5
 
 
+def test_config4_full_size_samples(dl):
+    """BASELINE config 4 at full size (4096x4096): FTLE of bead_on_a_rotating_hoop t=(0,2) and
+    of duffing_oscillator t=(10,0) (step counts 476..2456 per seed) against the C oracle on a
+    strided sample, and TrajectoryRepulsionRate(bead) against the oracle on crops."""
+    from oracle import c_oracle as co
+    from oracle import py_oracle as po
+
+    D, fl = dl.diagnostics, dl.flows
+    xb, yb = np.linspace(-1, 1, 4096) * 3, np.linspace(-1, 1, 4096) * 2.5
+    xd = yd = np.linspace(-2, 2, 4096)
+    for name, f, x, y, t in (("bead_on_a_rotating_hoop", fl.bead_on_a_rotating_hoop, xb, yb, (0.0, 2.0)),
+                             ("duffing_oscillator", fl.duffing_oscillator, xd, yd, (10.0, 0.0))):
+        d = D.FTLE()
+        field = np.ma.getdata(d.compute(x, y, f, t, edge_order=2, rtol=1e-8, atol=1e-8))
+        assert np.isfinite(field).all() and d.stats["failed"] == 0
+        ref, nfev, st = co.flow_map(name, po.flow_params(name), x[::64], y[::64], t[0], t[1], 1e-8, 1e-8)
+        got = d.flow_map[::64, ::64]
+        assert (np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)).max() < 1e-7, name  # 10 * rtol
+        # stencil rows recomputed by numpy on the GPU flow map (interior band)
+        lo, hi = 1000, 1040
+        rows = np.ma.getdata(po.ftle_from_flow_map(d.flow_map[lo - 2:hi + 2], x, y[lo - 2:hi + 2], t, 2))
+        assert rel_err(field[lo:hi], rows[2:-2], 1e-3).max() < 1e-8, name
+    tr = D.TrajectoryRepulsionRate()
+    rho = tr.compute(xb, yb, f=fl.bead_on_a_rotating_hoop, t=0, edge_order=2)
+    assert rho.shape == (4096, 4096)
+    u, v = tr.u, tr.v
+    gs = max(np.abs(u).max(), np.abs(v).max()) / (xb[1] - xb[0])
+    for (i0, j0) in ((0, 0), (2048 - 20, 2048 - 20), (4096 - 40, 4096 - 40)):
+        sl = (slice(i0, i0 + 40), slice(j0, j0 + 40))
+        ref = po.trajectory_repulsion_vec(xb[sl[1]], yb[sl[0]], u=u[sl], v=v[sl], edge_order=2)
+        inner = (slice(1, -1), slice(1, -1)) if 0 < i0 < 4000 else (
+            (slice(0, -1), slice(0, -1)) if i0 == 0 else (slice(1, None), slice(1, None)))
+        a, b = rho[sl][inner], ref[inner]
+        assert np.array_equal(np.ma.getmaskarray(a), np.ma.getmaskarray(b))
+        m = ~np.ma.getmaskarray(b)
+        assert np.abs(np.ma.getdata(a)[m] - np.ma.getdata(b)[m]).max() < 1e-10 * gs
+
+
+def test_config5_time_sweep_full_grid(dl):
+    """BASELINE config 5 pattern on the full 4096x2048 grid, T = 20 (3 of the 64 slices):
+    strided samples of every slice against the C oracle; ridge field produced on the device."""
+    from dynlab_b200.sweep import ftle_time_sweep
+    from oracle import c_oracle as co
+    from oracle import py_oracle as po
+
+    x, y = np.linspace(0, 2, 4096), np.linspace(0, 1, 2048)
+    spans = [(k * 10 / 64 + 20.0, k * 10 / 64) for k in (0, 21, 63)]
+    res = ftle_time_sweep(x, y, dl.flows.double_gyre, spans, edge_order=2, percentile=80, ridge=True,
+                          to_host=False, rtol=1e-8, atol=1e-8)
+    p = po.flow_params("double_gyre")
+    for k, span in enumerate(spans):
+        ftle, dd, mask = res[k]
+        assert ftle.is_cuda and ftle.shape == (2048, 4096)
+        fm, _, st = co.flow_map("double_gyre", p, x[::128], y[::128], span[0], span[1], 1e-8, 1e-8)
+        fo = co.ftle(fm, y[::128], x[::128], span[0], span[1], 2)  # coarse-grid FTLE: only for scale
+        assert np.isfinite(fo).all() and (st == 0).all()
+        f_host = ftle.cpu().numpy()
+        assert np.isfinite(f_host).all() and f_host.min() >= 0.0
+        frac_masked = mask.float().mean().item()
+        assert 0.8 <= frac_masked < 1.0  # percentile 80 + concavity/positivity masks
+        # FTLE on the full grid vs the oracle on a dense patch
+        i0, j0 = 700, 1500
+        pf, _, _ = co.flow_map("double_gyre", p, x[j0:j0 + 40], y[i0:i0 + 40], span[0], span[1], 1e-8, 1e-8)
+        ref = co.ftle(pf, y[i0:i0 + 40], x[j0:j0 + 40], span[0], span[1], 2)
+        got = f_host[i0 + 1:i0 + 39, j0 + 1:j0 + 39]
+        assert rel_err(got, ref[1:-1, 1:-1], 1e-3).max() < 1e-6
+
+
 def test_eulerian_c2_full_size_properties(dl):
     """BASELINE config 2 (8192x8192 bickley_jet, edge_order 2): crops vs the oracle; and
     attraction + repulsion = trace(S) = du/dx + dv/dy = 0 for this (divergence-free) jet."""
