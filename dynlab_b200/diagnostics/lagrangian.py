@@ -57,7 +57,11 @@ class FTLE(LagrangianDiagnostic2D):
                 and np.size(y) >= 64 * self.pipeline_chunks and np.size(x) * np.size(y) >= (1 << 22)):
             return self._compute_pipelined(self._plan(x, y, f, t, kwargs), t, edge_order)
         field = self._run(x, y, f, t, edge_order, self.gather_flow_map, kwargs)
-        self.field = np.ma.MaskedArray(Engine.get().to_host(field))
+        if sharding.host_result_wanted():
+            self.field = np.ma.MaskedArray(Engine.get().to_host(field))
+        else:  # sharding.set_host_result("rank0") on a non-zero rank: placeholder, all masked
+            torch.cuda.current_stream(field.device).synchronize()
+            self.field = np.ma.MaskedArray(np.broadcast_to(np.nan, tuple(field.shape)), mask=True)
         self._collect_stats()
         return self.field
 
