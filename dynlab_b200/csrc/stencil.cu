@@ -19,6 +19,7 @@
 // (true divisions), so the kernels have no FP64 divides on the interior path; sqrt and log
 // are branch-free MUFU-seeded Newton / series versions.  Grids are multiples of the SM count
 // and warps grid-stride over (strip, row-chunk) tasks.
+#include <math.h>
 #include <math_constants.h>
 
 #include <mutex>
@@ -262,12 +263,14 @@ __device__ __forceinline__ double fast_sqrt(double x) {
 
 // Constants of fast_log_ge1 in constant memory (a 64-bit literal costs two UMOVs per use on
 // sm_100a; the first ncu capture of this kernel showed 14 % of its instructions were UMOV).
-__constant__ double ST_LOGK[12] = {
+__constant__ double ST_LOGK[19] = {
     2.0 / 19.0, 2.0 / 17.0, 2.0 / 15.0, 2.0 / 13.0, 2.0 / 11.0, 2.0 / 9.0, 2.0 / 7.0, 2.0 / 5.0,
     2.0 / 3.0,
     6.93147180369123816490e-01,  // ln2 high part (exact when multiplied by |e| < 2^11)
     1.90821492927058770002e-10,  // ln2 low part
     1.4142135623730951,          // sqrt(2)
+    // ln1p(r) = r + r^2 (-1/2 + r/3 - r^2/4 + ... - r^6/8), Horner from the top  [12..18]
+    -1.0 / 8.0, 1.0 / 7.0, -1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0, -1.0 / 2.0,
 };
 
 // ln(x) for finite x >= 1 (the FTLE clamp guarantees it): x = 2^e m, m in [sqrt(1/2), sqrt 2),
@@ -316,11 +319,34 @@ int num_sms() {
   return g_sms;
 }
 
+// Table-driven ln(x), x >= 1 finite: x = 2^e m, m in [1, 2), c = 1 + i/128 with i the top seven
+// mantissa bits; ln x = e ln2 + ln c + ln1p(r), r = m / c - 1 in [0, 2^-7).  The table holds
+// (fl(1/c), -ln(fl(1/c))) so that the rounding of 1/c cancels; entry 0 is (1, 0), which keeps
+// full relative accuracy for x -> 1.  13 FP64 instructions instead of 27 for the series
+// version: the FTLE kernel is co-limited by the FP64 pipe (sqrt + log per point).
+__device__ double2 g_logtab[128];
+
+__device__ __forceinline__ double fast_log_ge1_tab(double x, const double2* tab) {
+  const int hi = __double2hiint(x);
+  const int e = (hi >> 20) - 1023;
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double2 t = tab[(hi >> 13) & 0x7f];
+  const double r = fma(m, t.x, -1.0);
+  double q = ST_LOGK[12];
+#pragma unroll
+  for (int k = 13; k <= 18; ++k) q = fma(q, r, ST_LOGK[k]);  // -1/8 ... -1/2
+  const double ed = (double)e;
+  const double hi_part = fma(ed, ST_LOGK[9], t.y);
+  const double lo_part = fma(ed, ST_LOGK[10], fma(r * r, q, r));
+  return hi_part + lo_part;
+}
+
 // Per-point epilogue shared by the interior and the edge kernels.
 // MODE: for KIND_FTLE unused; for KIND_EULER one of dlb_euler_mode.
 template <int KIND, int MODE, bool XI>
 __device__ __forceinline__ void emit(const StencilParams& P, double2 C, double d0dx, double d1dx,
-                                     double d0dy, double d1dy, long long o) {
+                                     double d0dy, double d1dy, long long o,
+                                     const double2* logtab = nullptr) {
   if (KIND == KIND_FTLE) {
     // JF = [[dfxdx, dfxdy], [dfydx, dfydy]], C = JF^T JF   (lagrangian.py:65-66)
     const double c11 = fma(d0dx, d0dx, d1dx * d1dx);
@@ -337,7 +363,9 @@ __device__ __forceinline__ void emit(const StencilParams& P, double2 C, double d
     // lagrangian.py:70-73; huge / non-finite lambda (blown-up trajectories): library log
     double out = 0.0;
     if (lam >= 1.0)
-      out = P.scale * ((lam < 1.0e300) ? fast_log_ge1(lam) : log(lam));
+      out = P.scale * ((lam < 1.0e300)
+                           ? (logtab ? fast_log_ge1_tab(lam, logtab) : fast_log_ge1(lam))
+                           : log(lam));
     else if (lam != lam)
       out = lam;  // NaN propagates like np.log
     P.field[o] = out;
@@ -577,8 +605,10 @@ __global__ void __launch_bounds__(TB_THREADS, 8)
   __shared__ __align__(128) double ring[TB_SLOTS][2 * TB_THREADS];
   __shared__ __align__(8) unsigned long long full[TB_SLOTS];
   __shared__ double2 ysm[TB_ROWS][2];
+  __shared__ double2 logtab_s[KIND == KIND_FTLE ? 128 : 1];
   const long long xdim = P.ax.n, ydim = P.ay.n;
   const int t = threadIdx.x;
+  if (KIND == KIND_FTLE) logtab_s[t] = g_logtab[t];  // TB_THREADS == 128 entries
   const long long r_lo = (P.out_row0 > 1) ? P.out_row0 : 1;
   const long long r_hi = (P.out_row0 + P.out_rows < ydim - 1) ? P.out_row0 + P.out_rows : ydim - 1;
   const long long ncols_out = xdim - 2;
@@ -661,7 +691,8 @@ __global__ void __launch_bounds__(TB_THREADS, 8)
         d0dy = fma(ycz.x, D.x, fma(yab.y, C.x, yab.x * U.x));
         d1dy = fma(ycz.x, D.y, fma(yab.y, C.y, yab.x * U.y));
       }
-      if (emit_thread) emit<KIND, MODE, XI>(P, C, d0dx, d1dx, d0dy, d1dy, o);
+      if (emit_thread)
+        emit<KIND, MODE, XI>(P, C, d0dx, d1dx, d0dy, d1dy, o, KIND == KIND_FTLE ? logtab_s : nullptr);
       o += xdim;
       U = C;
       C = D;
@@ -718,8 +749,32 @@ __global__ void __launch_bounds__(ST_BLOCK) stencil_edge_kernel(const StencilPar
   }
 }
 
+// (fl(1/c), -ln(fl(1/c))) for c = 1 + i/128, uploaded once per process and device.
+int ensure_logtab() {
+  static std::mutex mu;
+  static int done_dev = -1;
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  DLB_CUDA_CHECK(cudaGetDevice(&dev));
+  if (done_dev == dev) return DLB_OK;
+  double2 h[128];
+  for (int i = 0; i < 128; ++i) {
+    const double c = 1.0 + i / 128.0;
+    const double inv = (i == 0) ? 1.0 : 1.0 / c;
+    h[i].x = inv;
+    h[i].y = (i == 0) ? 0.0 : (double)(-logl((long double)inv));
+  }
+  DLB_CUDA_CHECK(cudaMemcpyToSymbol(g_logtab, h, sizeof(h)));
+  done_dev = dev;
+  return DLB_OK;
+}
+
 template <int KIND, int MODE, bool XI, class Loader>
 int launch_stencil(const StencilParams& P, const Loader& ld, cudaStream_t stream) {
+  if (KIND == KIND_FTLE) {
+    const int rc = ensure_logtab();
+    if (rc) return rc;
+  }
   const long long xdim = P.ax.n, ydim = P.ay.n;
   // edges
   const long long r0 = P.out_row0, r1 = P.out_row0 + P.out_rows;
