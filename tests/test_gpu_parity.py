@@ -481,6 +481,23 @@ def test_small_and_degenerate_grids(dl):
     assert d.x.dtype.kind == "i" and np.allclose(rv.FTLE_EXPECTED, f)
 
 
+def test_negative_and_sign_crossing_time_spans(dl):
+    """Time intervals with negative times and crossing t = 0, both directions (the step-size
+    floor uses the spacing of doubles at t in the direction of integration)."""
+    from oracle import py_oracle as po
+
+    x, y = np.linspace(-1.5, 1.5, 9), np.linspace(-1.0, 1.0, 7)
+    for name, kw in (("duffing_oscillator", {}), ("double_gyre", {}), ("pendulum", {})):
+        for span in ((-3.0, 2.0), (2.0, -3.0), (-4.0, -1.0), (-1.0, -4.0), (0.0, -2.5)):
+            d = dl.diagnostics.FTLE()
+            d.compute(x, y, getattr(dl.flows, name), span, edge_order=2, rtol=1e-8, atol=1e-8)
+            ref = po.flow_map(x, y, po.flow(name), span, rtol=1e-8, atol=1e-8)
+            assert (np.abs(d.flow_map - ref) / np.maximum(np.abs(ref), 1.0)).max() < 1e-9, (name, span)
+            nfev = sum(po.rk45_stats(po.flow(name), span, (xx, yy), rtol=1e-8, atol=1e-8)[1]
+                       for yy in y for xx in x)
+            assert d.stats["nfev"] == nfev, (name, span)
+
+
 def test_single_trajectory_wrappers(dl):
     """utils.odeint_wrapper / rk45_wrapper keep the integrator protocol (R:utils.py:6-25)."""
     from oracle import py_oracle as po
