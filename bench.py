@@ -332,6 +332,8 @@ def run_ours(args):
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak_flops / 1e12,
                          "unit": "TFLOP/s", "frac": achieved / peak_flops,
                          "traffic": dram("rk45_kernel"),
+                         "fp64_pipe_active_pct_ncu": (traffic.get("rk45_kernel") or {}).get(
+                             "fp64_pipe_active_pct"),
                          "kernel": "rk45_kernel<double_gyre> (K1)",
                          "note": "algorithmic FLOP = attempts*872 + seeds*256 (SURVEY §8d model, "
                                  "attempts counted by the kernel); peak = DFMA chain measured "

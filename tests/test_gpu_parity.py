@@ -213,6 +213,56 @@ def test_ftle_stencil_alone(dl, golden):
     assert rel_err(out.cpu().numpy(), gc["field"], 1e-3).max() < 1e-11
 
 
+def test_stencils_on_random_grids(dl):
+    """K2 / K3 (bulk-copy and register-window interior kernels + edge kernel) against numpy on
+    seeded random fields over random shapes (2..300, odd and even), uniform / non-uniform axes
+    and both edge orders — tails of strips, row chunks and ring refills included."""
+    import os
+
+    from dynlab_b200 import _native as nat
+    from dynlab_b200._engine import Engine
+    from oracle import py_oracle as po
+
+    eng = Engine.get()
+    rng = np.random.default_rng(20261020)
+    shapes = [(2, 2), (3, 3), (2, 9), (9, 2), (3, 130), (130, 3), (64, 126), (65, 127), (66, 128), (67, 129),
+              (129, 255), (200, 300), (131, 254)]
+    shapes += [tuple(int(v) for v in rng.integers(4, 300, 2)) for _ in range(12)]
+    try:
+        for bulk in ("1", "0"):
+            os.environ["DLB_STENCIL_BULK"] = bulk
+            for (ny, nx) in shapes:
+                ux, uy = bool(rng.integers(2)), bool(rng.integers(2))
+                x = np.arange(nx) * 0.37 if ux else np.sort(rng.uniform(0, 10, nx))
+                y = np.arange(ny) * 0.5 - 3 if uy else np.sort(rng.uniform(-5, 5, ny))
+                eo = int(rng.integers(1, 3))
+                if min(nx, ny) < eo + 1:
+                    eo = 1
+                fm = rng.normal(size=(ny, nx, 2)) * 3
+                gs = np.abs(fm).max() / min(np.diff(x).min(), np.diff(y).min())
+                out, _ = eng.ftle_stencil(torch.tensor(fm, device=eng.device), 0, x, y, eo, 2.0, 0, ny)
+                ref = np.ma.getdata(po.ftle_from_flow_map(fm, x, y, (0, 2.0), eo))
+                # ln(lambda) with lambda ~ gs^2: compare in absolute terms scaled by the rounding
+                # noise of the gradients (eps * |f| / dx relative to the gradient)
+                assert np.abs(out.cpu().numpy() - ref).max() < 1e-9, (bulk, ny, nx, eo, ux, uy)
+                u, v = fm[..., 0].copy(), fm[..., 1].copy()
+                v[rng.integers(ny), rng.integers(nx)] = 0.0
+                u[v == 0.0] = 0.0  # a zero-velocity node: masked by rate / ratio
+                ud, vd = torch.tensor(u, device=eng.device), torch.tensor(v, device=eng.device)
+                for mode, idx in ((nat.EULER_S_MIN, 0), (nat.EULER_S_MAX, -1)):
+                    f, _, _ = eng.euler_stencil(mode, ud, vd, 0, x, y, eo, 0, ny)
+                    r = np.ma.getdata(po.attraction_repulsion_rate(x, y, u=u, v=v, edge_order=eo, eigenvalue_index=idx))
+                    assert np.abs(f.cpu().numpy() - r).max() < 1e-12 * gs, (bulk, ny, nx, eo, mode)
+                for mode, rr in ((nat.EULER_RATE, "rate"), (nat.EULER_RATIO, "ratio")):
+                    f, m, _ = eng.euler_stencil(mode, ud, vd, 0, x, y, eo, 0, ny)
+                    r = po.trajectory_repulsion_vec(x, y, u=u, v=v, edge_order=eo, rate_or_ratio=rr)
+                    mk = np.ma.getmaskarray(r)
+                    assert np.array_equal(m.cpu().numpy().astype(bool), mk) and mk.any()
+                    assert np.abs(f.cpu().numpy() - np.ma.getdata(r))[~mk].max() < 4e-12 * gs
+    finally:
+        os.environ.pop("DLB_STENCIL_BULK", None)
+
+
 def test_stencil_slabs_match_full_grid(dl, golden):
     """Row-slab geometry of the C-ABI (grow0 / nloc / halo): any partition gives the bits of
     the single-slab result (this is what each rank runs in the multi-GPU path)."""
