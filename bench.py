@@ -347,6 +347,14 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_c_port()
+            # the reference's own Python path on the same cores (small strided samples):
+            # default LSODA integrator and the like-for-like scipy RK45 integrator
+            v_lsoda, _, smp, _ = reference_python_port(4096, "lsoda")
+            v_rk45, _, _, _ = reference_python_port(4096, "rk45")
+            line["cpu_baseline"]["python_reference_port"] = {
+                "lsoda_seeds_per_s": v_lsoda, "rk45_seeds_per_s": v_rk45, "sample": smp,
+                "what": "oracle/py_oracle.py: scipy per seed through a process pool over all "
+                        "cores + np.gradient + np.linalg.eig (what a dynlab user runs)"}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
