@@ -107,7 +107,8 @@ def _cell_segments(zd, mask, above, level):
 
 
 def marching_squares(x, y, z, level=0.0):
-    """Trace the ``level`` contour of ``z[ydim, xdim]`` (masked array or ndarray)."""
+    """Trace the ``level`` contour of ``z[ydim, xdim]`` (masked array or ndarray) entirely on the
+    host: numpy case analysis of every cell, then polyline linking."""
     zd = np.ma.getdata(z).astype(float)
     mask = np.ma.getmaskarray(z) | ~np.isfinite(zd)
     ny, nx = zd.shape
@@ -117,25 +118,10 @@ def marching_squares(x, y, z, level=0.0):
     segs = _cell_segments(zd, mask, above, level)
     if segs.shape[0] == 0:
         return []
-    # scan order of the owning cell
-    order = np.lexsort((segs[:, 1], segs[:, 0]))
-    segs = segs[order]
-    n = segs.shape[0]
+    nn = nx * ny
 
     def edge_key(p, q):
-        lo, hi = np.minimum(p, q), np.maximum(p, q)
-        return lo * (nx * ny) + hi
-
-    start_key = edge_key(segs[:, 2], segs[:, 3])
-    end_key = edge_key(segs[:, 4], segs[:, 5])
-    # successor: the segment that starts on the edge this one ends on
-    sorter = np.argsort(start_key, kind="stable")
-    pos = np.searchsorted(start_key[sorter], end_key)
-    pos_c = np.minimum(pos, n - 1)
-    has_next = (pos < n) & (start_key[sorter][pos_c] == end_key)
-    nxt = np.where(has_next, sorter[pos_c], -1)
-    has_prev = np.zeros(n, dtype=bool)
-    has_prev[nxt[has_next]] = True
+        return np.minimum(p, q) * nn + np.maximum(p, q)
 
     # vertex on an edge (p, q): linear interpolation to z == level
     def vertex(p, q):
@@ -147,36 +133,63 @@ def marching_squares(x, y, z, level=0.0):
 
     sx, sy = vertex(segs[:, 2], segs[:, 3])
     ex, ey = vertex(segs[:, 4], segs[:, 5])
+    cell = segs[:, 0] * (nx - 1) + segs[:, 1]
+    return link_segments(cell, edge_key(segs[:, 2], segs[:, 3]), edge_key(segs[:, 4], segs[:, 5]),
+                         np.stack([sx, sy, ex, ey], axis=1))
+
+
+def link_segments(cell, start_key, end_key, pts):
+    """Chain contour segments into polylines.  ``cell`` is the row-major index of the cell a
+    segment lies in, ``start_key`` / ``end_key`` identify the cell edges it starts / ends on
+    (shared edges have equal keys), ``pts[n, 4]`` holds its two vertices.  Lines come out in
+    the scan order of the cell they start in; closed loops repeat their first vertex."""
+    n = len(cell)
+    if n == 0:
+        return []
+    order = np.lexsort((start_key, cell))  # scan order of the owning cell, deterministic inside
+    cell, start_key, end_key, pts = cell[order], start_key[order], end_key[order], pts[order]
+    sorter = np.argsort(start_key, kind="stable")
+    sk_sorted = start_key[sorter]
+    pos = np.searchsorted(sk_sorted, end_key)
+    pos_c = np.minimum(pos, n - 1)
+    has_next = (pos < n) & (sk_sorted[pos_c] == end_key)
+    nxt = np.where(has_next, sorter[pos_c], -1)
+    has_prev = np.zeros(n, dtype=bool)
+    has_prev[nxt[has_next]] = True
 
     nxt_l = nxt.tolist()
     used = np.zeros(n, dtype=bool)
-    lines = []
-    starts = np.flatnonzero(~has_prev)  # open lines, already in scan order of their first cell
-    loops_from = 0
-    heads = [(int(s), False) for s in starts]
-    # closed loops: every segment not reachable from an open start; visit in scan order
-    for s, _ in heads:
+    heads = [int(s) for s in np.flatnonzero(~has_prev)]  # open lines start where nothing leads in
+    for s in heads:
         k = s
         while k != -1 and not used[k]:
             used[k] = True
             k = nxt_l[k]
-    for k0 in range(n):
+    for k0 in range(n):  # closed loops: whatever is left, entered at their first cell in scan order
         if not used[k0]:
-            heads.append((k0, True))
+            heads.append(k0)
             k = k0
             while not used[k]:
                 used[k] = True
                 k = nxt_l[k]
-    # emit in scan order of the starting cell (segments are sorted by cell)
-    heads.sort(key=lambda h: h[0])
-    for s, closed in heads:
+    heads.sort()
+    lines = []
+    for s in heads:
         idx = [s]
         k = nxt_l[s]
         while k != -1 and k != s:
             idx.append(k)
             k = nxt_l[k]
         idx = np.asarray(idx)
-        px = np.concatenate([[sx[s]], ex[idx]])
-        py = np.concatenate([[sy[s]], ey[idx]])
+        px = np.concatenate([[pts[s, 0]], pts[idx, 2]])
+        py = np.concatenate([[pts[s, 1]], pts[idx, 3]])
         lines.append(np.stack([px, py], axis=1))
     return lines
+
+
+def zero_contour_lines_device(eng, z_dev, mask_dev, x, y, level: float = 0.0):
+    """Device case analysis (csrc/contour.cu) + host linking.  ``z_dev`` / ``mask_dev`` are the
+    device tensors of the (masked) field; nothing but the O(ridge length) segment records
+    crosses PCIe."""
+    cell, ka, kb, pts = eng.contour_segments(z_dev, mask_dev, x, y, level)
+    return link_segments(cell, ka, kb, pts)

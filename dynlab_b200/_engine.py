@@ -224,6 +224,33 @@ class Engine:
                 conc.data_ptr(), mask.data_ptr(), scratch.data_ptr(), ws, wsz, self.stream()))
         return dd, conc, mask
 
+    # -- contour segments -------------------------------------------------------------
+    def contour_segments(self, z, mask, x, y, level=0.0):
+        """Device pass of the contour extraction: returns host arrays (cell, key_a, key_b,
+        pts[n, 4]) of the segments of the ``level`` contour of ``z`` (device tensor [ydim, xdim];
+        ``mask`` uint8 device tensor or None)."""
+        xdim, ydim = len(x), len(y)
+        with torch.cuda.device(self.device):
+            ws, wsz = self.workspace(xdim, ydim)
+            cap = max(1 << 16, 8 * (xdim + ydim))
+            count = torch.zeros(1, dtype=torch.int64, device=self.device)
+            while True:
+                cell = self.empty(cap, dtype=torch.int64)
+                ka, kb = self.empty(cap, dtype=torch.int64), self.empty(cap, dtype=torch.int64)
+                pts = self.empty(cap, 4)
+                with self._timed("contour_segments"):
+                    nat.check(nat.lib.dlb_contour_segments(
+                        z.data_ptr(), mask.data_ptr() if mask is not None else None, nat.dptr(x),
+                        xdim, nat.dptr(y), ydim, float(level), cell.data_ptr(), ka.data_ptr(),
+                        kb.data_ptr(), pts.data_ptr(), cap, count.data_ptr(), ws, wsz,
+                        self.stream()))
+                n = int(count.item())
+                if n <= cap:
+                    break
+                cap = n + n // 8
+        return (cell[:n].cpu().numpy(), ka[:n].cpu().numpy(), kb[:n].cpu().numpy(),
+                pts[:n].cpu().numpy())
+
     # -- FP64 peak --------------------------------------------------------------------
     def dfma_peak(self, iters: int = 4096):
         fl, ms = C.c_double(0.0), C.c_double(0.0)

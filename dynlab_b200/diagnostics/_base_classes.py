@@ -274,7 +274,7 @@ class RidgeExtractor2D(Diagnostic2D, ABC):
         """``field`` / ``Xi``: device tensors ``[ydim, xdim]`` / ``[ydim, xdim, 2]``.
         The gradient/Hessian/mask stage runs on the device; the zero-contour of the masked
         directional-derivative field is traced on the host (O(ridge length) output)."""
-        from .._contour import zero_contour_lines
+        from .. import _contour
 
         eng = Engine.get()
         threshold = None
@@ -282,9 +282,15 @@ class RidgeExtractor2D(Diagnostic2D, ABC):
             # R:_base_classes.py:266-268 — np.percentile of the (unmasked) field values
             threshold = float(np.percentile(eng.to_host(field), percentile))
         dd, conc, mask = eng.ridge_field(field, Xi, self._xf, self._yf, edge_order, threshold)
-        dd_h = np.ma.MaskedArray(eng.to_host(dd), mask=eng.to_host(mask).astype(bool))
-        ridge_lines = zero_contour_lines(self.x, self.y, dd_h)
+        dd_h = None
+        if _contour._contourpy_generator is not None:  # pragma: no cover - the reference's own
+            dd_h = np.ma.MaskedArray(eng.to_host(dd), mask=eng.to_host(mask).astype(bool))
+            ridge_lines = _contour.zero_contour_lines(self.x, self.y, dd_h)
+        else:  # cell classification on the device, polyline linking on the host
+            ridge_lines = _contour.zero_contour_lines_device(eng, dd, mask, self._xf, self._yf)
         if debug:
+            if dd_h is None:
+                dd_h = np.ma.MaskedArray(eng.to_host(dd), mask=eng.to_host(mask).astype(bool))
             self.directional_derivative = dd_h
             self.concavity = np.ma.MaskedArray(eng.to_host(conc))
         return ridge_lines

@@ -14,6 +14,7 @@ import torch.distributed as dist
 
 from . import _native as nat
 from . import sharding
+from ._contour import zero_contour_lines_device
 from ._engine import Engine, as_coord
 from ._resolve import resolve_flow
 from .utils import ODEINT_DEFAULT_TOL, parse_integrator_kwargs
@@ -25,8 +26,10 @@ def ftle_time_sweep(x, y, f, t_spans, edge_order: int = 1, percentile=None, ridg
 
     Returns ``{slice_index: result}`` for the slices this rank owns (all of them without a
     process group).  ``result`` is the FTLE field (``np.ma.MaskedArray`` or a device tensor);
-    with ``ridge=True`` it is ``(ftle, directional_derivative, ridge_mask)`` — the input of the
-    contour step of ``LCS`` (R:_base_classes.py:216-268) with ``percentile`` applied.
+    with ``ridge=True`` it is ``(ftle, directional_derivative, lines)`` (host) or ``(ftle,
+    directional_derivative, ridge_mask, lines)`` (device tensors + host polylines): the ridge
+    field of ``LCS`` (R:_base_classes.py:216-268) with ``percentile`` applied and its zero
+    contour (device cell classification + host linking), i.e. what ``LCS.compute`` returns.
     """
     xs, ys = as_coord(np.asarray(x).squeeze()), as_coord(np.asarray(y).squeeze())
     if xs.ndim != 1 or ys.ndim != 1:
@@ -61,9 +64,11 @@ def ftle_time_sweep(x, y, f, t_spans, edge_order: int = 1, percentile=None, ridg
             # R:_base_classes.py:266-268 — np.percentile of the (unmasked) field values
             thr = float(np.percentile(eng.to_host(field), percentile))
         dd, conc, mask = eng.ridge_field(field, xi, xs, ys, edge_order, thr)
+        lines = zero_contour_lines_device(eng, dd, mask, xs, ys)
         if to_host:
             out[k] = (np.ma.MaskedArray(eng.to_host(field)),
-                      np.ma.MaskedArray(eng.to_host(dd), mask=eng.to_host(mask).astype(bool)))
+                      np.ma.MaskedArray(eng.to_host(dd), mask=eng.to_host(mask).astype(bool)),
+                      lines)
         else:
-            out[k] = (field, dd, mask)
+            out[k] = (field, dd, mask, lines)
     return out

@@ -177,6 +177,22 @@ int dlb_ridge_field(const double* d_field, const double* d_xi, const double* h_x
                     double threshold, double* d_dd, double* d_conc, uint8_t* d_mask,
                     double* d_scratch, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Contour segments — the O(cells) part of contourpy's
+ * `contour_generator(x, y, z).lines(level)` (R:src/dynlab/diagnostics/_base_classes.py:270) on the
+ * device: for every grid cell the `level` contour crosses, records (cell index, start-edge key,
+ * end-edge key, start vertex, end vertex) with contourpy's conventions (upper iff z > level,
+ * corner masking, saddles by the cell-centre mean, upper region on the left).  d_mask ([ydim]
+ * [xdim] uint8, 1 = masked) may be NULL.  Records are appended in arbitrary order to d_cell /
+ * d_key_a / d_key_b ([max_segments] int64; an edge key is lo_node * xdim*ydim + hi_node) and d_pts
+ * ([max_segments][4]: sx, sy, ex, ey).  *d_count receives the number of segments found; if it
+ * exceeds max_segments only the first max_segments slots were written (call again with more
+ * room).  Linking segments into polylines is left to the host (O(ridge length)). */
+int dlb_contour_segments(const double* d_z, const uint8_t* d_mask, const double* h_x, int64_t xdim,
+                         const double* h_y, int64_t ydim, double level, int64_t* d_cell,
+                         int64_t* d_key_a, int64_t* d_key_b, double* d_pts, int64_t max_segments,
+                         uint64_t* d_count, void* d_workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* FP64 roofline denominator: runs a register-resident DFMA chain kernel and returns the
  * sustained FP64 throughput in FLOP/s (FMA = 2) through *flops_per_s.  Synchronises. */
 int dlb_dfma_peak(int iters, double* flops_per_s, double* elapsed_ms);

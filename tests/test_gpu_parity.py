@@ -435,7 +435,8 @@ def test_time_sweep_matches_single_calls(dl):
         l = dl.diagnostics.LCS()
         l.compute(x, y, f=dl.flows.double_gyre, t=spans[k], edge_order=2, percentile=80, debug=True,
                   rtol=1e-8, atol=1e-8)
-        ftle, dd = res[k]
+        ftle, dd, lines = res[k]
+        assert len(lines) == len(l.lcs) and all(np.array_equal(a, b) for a, b in zip(lines, l.lcs))
         assert np.array_equal(np.ma.getdata(ftle), np.ma.getdata(l.ftle))
         assert np.array_equal(np.ma.getmaskarray(dd), np.ma.getmaskarray(l.directional_derivative))
         assert np.array_equal(np.ma.getdata(dd), np.ma.getdata(l.directional_derivative))
@@ -478,6 +479,44 @@ def test_no_out_of_bounds_writes(dl):
                     assert not (fo[2:ny - 2] == canary).any()
     finally:
         os.environ.pop("DLB_STENCIL_BULK", None)
+
+
+def test_device_contour_segments_match_host_tracer(dl, golden):
+    """csrc/contour.cu (cell classification on the device) + host linking gives exactly the
+    polylines of the all-host tracer: the reference's ridge fields, random masked fields with
+    saddles, single masked nodes (corner triangles), closed loops, non-finite values."""
+    from dynlab_b200._contour import marching_squares, zero_contour_lines_device
+    from dynlab_b200._engine import Engine
+
+    eng = Engine.get()
+
+    def both(x, y, z):
+        zd = np.ma.getdata(z).astype(float)
+        mk = np.ma.getmaskarray(z)
+        host = marching_squares(x, y, z)
+        dev = zero_contour_lines_device(eng, torch.tensor(zd, device=eng.device),
+                                        torch.tensor(mk.astype(np.uint8), device=eng.device), x, y)
+        assert len(host) == len(dev)
+        for a, b in zip(host, dev):
+            assert np.array_equal(a, b)
+        return host
+
+    g = golden("contour_inputs")
+    for tag, exp in (("lcs", rv.LCS_LINES), ("iles_attracting", rv.ILES_FORCED_ATTRACTING),
+                     ("iles_raw_repelling", rv.ILES_REPELLING)):
+        lines = both(g["x"], g["y"], np.ma.MaskedArray(g[tag + "__dd"], mask=g[tag + "__mask"]))
+        assert len(lines) == len(exp) and all(np.isclose(a, b).all() for a, b in zip(exp, lines))
+    rng = np.random.default_rng(11)
+    for (ny, nx) in ((2, 2), (3, 7), (40, 33), (129, 200), (257, 511)):
+        x, y = np.sort(rng.uniform(0, 3, nx)), np.linspace(-1, 1, ny)
+        z = rng.normal(size=(ny, nx))                      # rough field: many saddles, loops
+        both(x, y, np.ma.MaskedArray(z, mask=rng.random((ny, nx)) < 0.15))
+        X, Y = np.meshgrid(x, y)
+        zs = np.sin(3 * X) * np.cos(4 * Y) + 0.1 * X       # smooth field: long lines and loops
+        zs[rng.integers(ny), rng.integers(nx)] = np.nan
+        assert len(both(x, y, np.ma.MaskedArray(zs, mask=(X - 1.5) ** 2 + Y ** 2 < 0.1))) >= (1 if ny > 3 else 0)
+    assert zero_contour_lines_device(eng, torch.ones(5, 5, dtype=torch.float64, device=eng.device), None,
+                                     np.arange(5.0), np.arange(5.0)) == []
 
 
 # ---------------------------------------------------------------- errors / edge cases
@@ -668,8 +707,9 @@ def test_config5_time_sweep_full_grid(dl):
                           to_host=False, rtol=1e-8, atol=1e-8)
     p = po.flow_params("double_gyre")
     for k, span in enumerate(spans):
-        ftle, dd, mask = res[k]
+        ftle, dd, mask, lines = res[k]
         assert ftle.is_cuda and ftle.shape == (2048, 4096)
+        assert len(lines) > 0 and all(l.ndim == 2 and l.shape[1] == 2 for l in lines)
         fm, _, st = co.flow_map("double_gyre", p, x[::128], y[::128], span[0], span[1], 1e-8, 1e-8)
         fo = co.ftle(fm, y[::128], x[::128], span[0], span[1], 2)  # coarse-grid FTLE: only for scale
         assert np.isfinite(fo).all() and (st == 0).all()
