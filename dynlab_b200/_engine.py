@@ -251,6 +251,49 @@ class Engine:
         return (cell[:n].cpu().numpy(), ka[:n].cpu().numpy(), kb[:n].cpu().numpy(),
                 pts[:n].cpu().numpy())
 
+    # -- percentile -------------------------------------------------------------------
+    def percentile(self, values, q):
+        """``np.percentile(values, q)`` (default 'linear' method) of a device tensor without
+        moving it: the two neighbouring order statistics come from the radix select in
+        csrc/select.cu, the interpolation below follows numpy's ``_quantile`` / ``_lerp``
+        expression by expression so the result is bit-identical
+        (numpy/lib/_function_base_impl.py: virtual index ``(n - 1) * q``, ``gamma = virtual -
+        floor(virtual)``, ``a + (b - a) * gamma`` or ``b - (b - a) * (1 - gamma)`` for
+        ``gamma >= 0.5``)."""
+        qf = np.true_divide(np.float64(q), 100)
+        if not (0.0 <= qf <= 1.0):
+            raise ValueError("Percentiles must be in the range [0, 100]")
+        n = values.numel()
+        if n == 0:
+            return float("nan")
+        virtual = (n - 1) * qf
+        prev = np.floor(virtual)
+        if virtual >= n - 1:
+            lo = hi = n - 1
+        else:
+            lo, hi = int(prev), int(prev) + 1
+        gamma = np.float64(virtual - prev)
+        with torch.cuda.device(self.device):
+            flat = values.reshape(-1)
+            if not flat.is_contiguous():
+                flat = flat.contiguous()
+            res = self.empty(3)  # [a_lo, a_hi, nan count (uint64 bits)]
+            nbytes = int(nat.lib.dlb_select_scratch_bytes())
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            ranks = (C.c_int64 * 2)(lo, hi)
+            with self._timed("order_statistics", 17):
+                nat.check(nat.lib.dlb_order_statistics(
+                    flat.data_ptr(), n, ranks, 2, res.data_ptr(), res[2:].data_ptr(),
+                    scratch.data_ptr(), nbytes, self.stream()))
+            host = res.cpu()
+        if int(host[2:].view(torch.int64)[0]) != 0:
+            return float("nan")
+        a, b = np.float64(host[0].item()), np.float64(host[1].item())
+        diff = np.subtract(b, a)
+        if gamma >= 0.5:
+            return float(np.subtract(b, diff * (1 - gamma)))
+        return float(np.add(a, diff * gamma))
+
     # -- FP64 peak --------------------------------------------------------------------
     def dfma_peak(self, iters: int = 4096):
         fl, ms = C.c_double(0.0), C.c_double(0.0)

@@ -279,8 +279,9 @@ class RidgeExtractor2D(Diagnostic2D, ABC):
         eng = Engine.get()
         threshold = None
         if percentile:
-            # R:_base_classes.py:266-268 — np.percentile of the (unmasked) field values
-            threshold = float(np.percentile(eng.to_host(field), percentile))
+            # R:_base_classes.py:266-268 — np.percentile of the (unmasked) field values, selected
+            # on the device (csrc/select.cu) and interpolated like numpy
+            threshold = eng.percentile(field, percentile)
         dd, conc, mask = eng.ridge_field(field, Xi, self._xf, self._yf, edge_order, threshold)
         dd_h = None
         if _contour._contourpy_generator is not None:  # pragma: no cover - the reference's own

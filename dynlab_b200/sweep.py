@@ -62,7 +62,7 @@ def ftle_time_sweep(x, y, f, t_spans, edge_order: int = 1, percentile=None, ridg
         thr = None
         if percentile:
             # R:_base_classes.py:266-268 — np.percentile of the (unmasked) field values
-            thr = float(np.percentile(eng.to_host(field), percentile))
+            thr = eng.percentile(field, percentile)
         dd, conc, mask = eng.ridge_field(field, xi, xs, ys, edge_order, thr)
         lines = zero_contour_lines_device(eng, dd, mask, xs, ys)
         if to_host:

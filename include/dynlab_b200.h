@@ -193,6 +193,18 @@ int dlb_contour_segments(const double* d_z, const uint8_t* d_mask, const double*
                          uint64_t* d_count, void* d_workspace, size_t workspace_bytes,
                          void* stream);
 
+/* Order statistics — the two neighbouring sorted values `np.percentile(field,
+ * percentile)` interpolates between (R:src/dynlab/diagnostics/_base_classes.py:266-268), found on
+ * the device by an 8-pass radix select instead of a full-field D2H copy + host partition.
+ * d_values [n] (any layout, read flat); h_ranks [nranks] (1 or 2 zero-based ranks in the sorted
+ * order, ascending); d_out [nranks] receives the selected elements (exact input values; -0.0 sorts
+ * before +0.0); *d_nan_count the number of NaNs in d_values (numpy returns NaN if it is non-zero;
+ * the ranks are then meaningless).  d_scratch: dlb_select_scratch_bytes() bytes. */
+size_t dlb_select_scratch_bytes(void);
+int dlb_order_statistics(const double* d_values, int64_t n, const int64_t* h_ranks, int nranks,
+                         double* d_out, uint64_t* d_nan_count, void* d_scratch,
+                         size_t scratch_bytes, void* stream);
+
 /* FP64 roofline denominator: runs a register-resident DFMA chain kernel and returns the
  * sustained FP64 throughput in FLOP/s (FMA = 2) through *flops_per_s.  Synchronises. */
 int dlb_dfma_peak(int iters, double* flops_per_s, double* elapsed_ms);

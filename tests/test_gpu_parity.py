@@ -481,6 +481,39 @@ def test_no_out_of_bounds_writes(dl):
         os.environ.pop("DLB_STENCIL_BULK", None)
 
 
+def test_device_percentile_bit_identical_to_numpy(dl):
+    """csrc/select.cu (radix select of the two neighbouring order statistics) + numpy's lerp
+    reproduces ``np.percentile`` (R:_base_classes.py:266-268) bit for bit: random signed fields,
+    heavy ties, +-0, infinities, tiny arrays, q at the ends, a real FTLE field; NaN -> NaN."""
+    from dynlab_b200._engine import Engine
+
+    eng = Engine.get()
+    rng = np.random.default_rng(5)
+
+    def check(a, qs):
+        d = torch.tensor(a, device=eng.device)
+        for q in qs:
+            got, exp = eng.percentile(d, q), float(np.percentile(a, q))
+            assert got == exp or (np.isnan(got) and np.isnan(exp)), (a.shape, q, got, exp)
+
+    qs = (0, 1e-9, 0.5, 10, 33.3, 50, 60, 80, 90, 99.9, 99.999999, 100)
+    check(rng.normal(size=(257, 513)), qs)
+    check(rng.normal(size=1_000_003) * 10.0 ** rng.integers(-300, 300, size=1_000_003), qs)
+    check(rng.integers(-3, 4, size=(100, 1000)).astype(float), qs)       # ties
+    check(np.array([0.0, -0.0, 0.0, -0.0, 1.0, -1.0, np.inf, -np.inf, 5e-324, -5e-324]), qs)
+    check(np.array([3.25]), qs)
+    check(np.array([2.0, -7.5]), qs)
+    check(np.abs(rng.normal(size=(2048, 4096))), (60, 80, 95))
+    with pytest.raises(ValueError):
+        eng.percentile(torch.zeros(4, device=eng.device, dtype=torch.float64), 101)
+    a = rng.normal(size=1000)
+    a[17] = np.nan
+    assert np.isnan(eng.percentile(torch.tensor(a, device=eng.device), 50))
+    x, y = np.linspace(0, 2, 301), np.linspace(0, 1, 151)
+    f = dl.diagnostics.FTLE().compute(x, y, dl.flows.double_gyre, (0, 8), edge_order=2)
+    check(np.ma.getdata(f), qs)
+
+
 def test_device_contour_segments_match_host_tracer(dl, golden):
     """csrc/contour.cu (cell classification on the device) + host linking gives exactly the
     polylines of the all-host tracer: the reference's ridge fields, random masked fields with
