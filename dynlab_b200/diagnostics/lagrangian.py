@@ -56,6 +56,8 @@ class FTLE(LagrangianDiagnostic2D):
         if (sharding.world()[1] == 1 and self.pipeline_chunks > 1
                 and np.size(y) >= 64 * self.pipeline_chunks and np.size(x) * np.size(y) >= (1 << 22)):
             return self._compute_pipelined(self._plan(x, y, f, t, kwargs), t, edge_order)
+        if sharding.host_result_shared():
+            return self._compute_shared(x, y, f, t, edge_order, kwargs)
         field = self._run(x, y, f, t, edge_order, self.gather_flow_map, kwargs)
         if sharding.host_result_wanted():
             self.field = np.ma.MaskedArray(Engine.get().to_host(field))
@@ -108,6 +110,35 @@ class FTLE(LagrangianDiagnostic2D):
         self.field_device = field
         self.field = np.ma.MaskedArray(host.numpy())
         self._counters_pending, self._counter_tensors = True, counters
+        self._collect_stats()
+        return self.field
+
+    def _compute_shared(self, x, y, f, t, edge_order, kwargs):
+        """Multi-GPU with ``sharding.set_host_result("shared")``: K1 and K2 on this rank's
+        slab, then one device-to-host copy of the slab's FTLE rows into the host segment all
+        ranks of the box map.  No device all-gather; the field crosses PCIe once in total.
+        ``flow_map`` / ``field_device`` hold this rank's rows only."""
+        keep, self.gather_flow_map = self.gather_flow_map, False
+        try:
+            local, slab = LagrangianDiagnostic2D.compute(self, x, y, f, t, **kwargs)
+        finally:
+            self.gather_flow_map = keep
+        if edge_order > 2:
+            raise ValueError("'edge_order' greater than 2 not supported")
+        t_span = abs(float(t[-1]) - float(t[0]))
+        if t_span == 0.0:
+            raise ZeroDivisionError("float division by zero")  # R:lagrangian.py:71
+        eng = Engine.get()
+        host_np, host_t = sharding.shared_host_array((self.ydim, self.xdim))
+        own = None
+        if slab.rows:
+            own, _ = eng.ftle_stencil(local, slab.lo, self._xf, self._yf, edge_order, t_span,
+                                      slab.row0, slab.rows, nat.XI_NONE)
+            host_t[slab.row0:slab.row0 + slab.rows].copy_(own, non_blocking=True)
+        torch.cuda.current_stream(eng.device).synchronize()
+        torch.distributed.barrier()  # every rank's rows are in the segment
+        self.field_device = own
+        self.field = np.ma.MaskedArray(host_np)
         self._collect_stats()
         return self.field
 

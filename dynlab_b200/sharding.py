@@ -8,8 +8,13 @@ rows, it never computes.
 """
 from __future__ import annotations
 
+import mmap
+import os
+import socket
+import uuid
 from dataclasses import dataclass
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -27,19 +32,69 @@ _host_result = "all"  # which ranks receive the gathered field in host memory
 
 
 def set_host_result(which) -> None:
-    """``"all"`` (default): every rank's ``compute`` returns the full field on the host, like
-    the single-process reference.  ``"rank0"``: only rank 0 copies it to the host (the other
-    ranks get a fully masked placeholder of the same shape) — at 8 GPUs the eight simultaneous
-    268 MB device-to-host copies of config 3 cost more than the whole computation."""
+    """``"all"`` (default): every rank's ``compute`` returns its own copy of the full field on
+    the host, like the single-process reference.  ``"rank0"``: only rank 0 copies it to the host
+    (the other ranks get a fully masked placeholder of the same shape) — at 8 GPUs the eight
+    simultaneous 268 MB device-to-host copies of config 3 cost more than the whole computation.
+    ``"shared"``: the ranks of the box share one pinned host segment (``shared_host_array``);
+    each rank copies only its own rows into it and every rank returns a view of the whole, so the
+    field crosses PCIe once instead of once per rank and no device all-gather is needed.  The
+    price is aliasing: the returned array is the same memory on every rank and the next
+    ``compute`` on a grid of the same size overwrites it — copy it if it must outlive that."""
     global _host_result
-    if which not in ("all", "rank0"):
-        raise ValueError('which must be "all" or "rank0"')
+    if which not in ("all", "rank0", "shared"):
+        raise ValueError('which must be "all", "rank0" or "shared"')
     _host_result = which
 
 
 def host_result_wanted() -> bool:
     rank, size = world()
-    return _host_result == "all" or size == 1 or rank == 0
+    return _host_result in ("all", "shared") or size == 1 or rank == 0
+
+
+def host_result_shared() -> bool:
+    return _host_result == "shared" and world()[1] > 1
+
+
+_segments = {}  # nbytes -> (mmap object, flat uint8 ndarray)
+
+
+def shared_host_array(shape, dtype=np.float64):
+    """Collective over the default process group: a host array of ``shape`` backed by one
+    POSIX shared-memory segment mapped by every rank of the box (page-locked for CUDA when a
+    device is in use, so slab copies into it run at PCIe speed).  Segments are cached by size
+    and reused by later calls; the name is unlinked as soon as every rank has mapped it, so
+    nothing is left in /dev/shm whatever happens to the job afterwards."""
+    rank, size = world()
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    seg = _segments.get(nbytes)
+    if seg is None:
+        hosts = [None] * size
+        dist.all_gather_object(hosts, socket.gethostname())
+        if len(set(hosts)) != 1:
+            raise RuntimeError('set_host_result("shared") needs all ranks on one box')
+        name = [f"/dev/shm/dynlab_b200_{uuid.uuid4().hex}" if rank == 0 else None]
+        fd = -1
+        if rank == 0:
+            fd = os.open(name[0], os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+            os.ftruncate(fd, max(nbytes, 1))
+        dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            fd = os.open(name[0], os.O_RDWR)
+        mm = mmap.mmap(fd, max(nbytes, 1))
+        os.close(fd)
+        flat = np.frombuffer(mm, dtype=np.uint8)
+        if rank == 0:
+            flat[:] = 0  # touch the pages once, here, not inside the first timed copy
+        dist.barrier()
+        if rank == 0:
+            os.unlink(name[0])
+        if torch.cuda.is_available() and dist.get_backend() == "nccl":
+            torch.cuda.check_error(
+                torch.cuda.cudart().cudaHostRegister(flat.ctypes.data, max(nbytes, 1), 0))
+        seg = _segments[nbytes] = (mm, flat)
+    arr = seg[1][:nbytes].view(dtype).reshape(shape)
+    return arr, torch.from_numpy(arr)
 
 
 def world():

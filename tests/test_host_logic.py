@@ -242,3 +242,46 @@ def test_sharded_halo_and_gather_gloo(tmp_path, size, ydim, edge_order):
     port = 29500 + (os.getpid() + size * 17 + ydim) % 2000
     mp.spawn(_shard_worker, args=(size, port, ydim, 9, edge_order, str(tmp_path)), nprocs=size, join=True)
     assert os.path.exists(tmp_path / f"ok_{size}_{ydim}_{edge_order}")
+
+
+def _shared_worker(rank, size, port, out_dir):
+    """sharding.shared_host_array: one segment mapped by every rank; each rank writes its own
+    rows, after a barrier every rank sees the whole array; the segment is cached by size and
+    its /dev/shm name is gone as soon as it is mapped."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    try:
+        from dynlab_b200 import sharding
+
+        sharding.set_host_result("shared")
+        assert sharding.host_result_shared() and sharding.host_result_wanted()
+        ydim, xdim = 11, 7
+        for rep in range(2):
+            arr, ten = sharding.shared_host_array((ydim, xdim))
+            assert arr.shape == (ydim, xdim) and arr.dtype == np.float64
+            slab = sharding.partition(ydim, size, rank)
+            rows = torch.arange(slab.row0, slab.row0 + slab.rows, dtype=torch.float64)
+            ten[slab.row0:slab.row0 + slab.rows] = (rows[:, None] * 100 + torch.arange(xdim) + rep)
+            dist.barrier()
+            exp = np.arange(ydim)[:, None] * 100.0 + np.arange(xdim) + rep
+            assert np.array_equal(arr, exp)
+            dist.barrier()
+        assert len(sharding._segments) == 1
+        assert not [n for n in os.listdir("/dev/shm") if n.startswith("dynlab_b200_")]
+        other, _ = sharding.shared_host_array((3, 5))
+        assert other.shape == (3, 5) and len(sharding._segments) == 2
+        sharding.set_host_result("all")
+        assert not sharding.host_result_shared()
+        with pytest.raises(ValueError):
+            sharding.set_host_result("everyone")
+        if rank == 0:
+            open(os.path.join(out_dir, "ok_shared"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("size", [2, 3])
+def test_shared_host_segment_gloo(tmp_path, size):
+    port = 31500 + (os.getpid() + size * 13) % 2000
+    mp.spawn(_shared_worker, args=(size, port, str(tmp_path)), nprocs=size, join=True)
+    assert os.path.exists(tmp_path / "ok_shared")
