@@ -109,15 +109,22 @@ def _cell_segments(zd, mask, above, level):
 def marching_squares(x, y, z, level=0.0):
     """Trace the ``level`` contour of ``z[ydim, xdim]`` (masked array or ndarray) entirely on the
     host: numpy case analysis of every cell, then polyline linking."""
+    rec = host_segments(x, y, z, level)
+    return link_segments(*rec) if rec is not None else []
+
+
+def host_segments(x, y, z, level=0.0):
+    """numpy twin of csrc/contour.cu: segment records (cell, start_key, end_key, pts[n, 4]) of
+    the ``level`` contour, or None when there are none."""
     zd = np.ma.getdata(z).astype(float)
     mask = np.ma.getmaskarray(z) | ~np.isfinite(zd)
     ny, nx = zd.shape
     if ny < 2 or nx < 2:
-        return []
+        return None
     above = (zd > level) & ~mask
     segs = _cell_segments(zd, mask, above, level)
     if segs.shape[0] == 0:
-        return []
+        return None
     nn = nx * ny
 
     def edge_key(p, q):
@@ -134,8 +141,8 @@ def marching_squares(x, y, z, level=0.0):
     sx, sy = vertex(segs[:, 2], segs[:, 3])
     ex, ey = vertex(segs[:, 4], segs[:, 5])
     cell = segs[:, 0] * (nx - 1) + segs[:, 1]
-    return link_segments(cell, edge_key(segs[:, 2], segs[:, 3]), edge_key(segs[:, 4], segs[:, 5]),
-                         np.stack([sx, sy, ex, ey], axis=1))
+    return (cell, edge_key(segs[:, 2], segs[:, 3]), edge_key(segs[:, 4], segs[:, 5]),
+            np.stack([sx, sy, ex, ey], axis=1))
 
 
 def link_segments(cell, start_key, end_key, pts):
@@ -187,9 +194,39 @@ def link_segments(cell, start_key, end_key, pts):
     return lines
 
 
+def link_segments_native(cell, start_key, end_key, pts, xdim, ydim):
+    """``link_segments`` in C++ (csrc/link.cu, ``dlb_link_segments``): same rules, same output,
+    without the per-segment Python loop."""
+    from . import _native as nat
+
+    n = len(cell)
+    if n == 0:
+        return []
+    cell = np.ascontiguousarray(cell, dtype=np.int64)
+    ka = np.ascontiguousarray(start_key, dtype=np.int64)
+    kb = np.ascontiguousarray(end_key, dtype=np.int64)
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    start = np.empty(n + 1, dtype=np.int64)
+    verts = np.empty((2 * n, 2), dtype=np.float64)
+    nl = np.zeros(1, dtype=np.int64)
+    nat.check(nat.lib.dlb_link_segments(cell.ctypes.data, ka.ctypes.data, kb.ctypes.data,
+                                        pts.ctypes.data, n, int(xdim), int(ydim), start.ctypes.data,
+                                        verts.ctypes.data,
+                                        nl.ctypes.data))
+    b = start[:int(nl[0]) + 1].tolist()
+    verts = verts[:b[-1]].copy()  # drop the unused tail; lines are views of this block
+    return [verts[b[i]:b[i + 1]] for i in range(len(b) - 1)]
+
+
 def zero_contour_lines_device(eng, z_dev, mask_dev, x, y, level: float = 0.0):
-    """Device case analysis (csrc/contour.cu) + host linking.  ``z_dev`` / ``mask_dev`` are the
-    device tensors of the (masked) field; nothing but the O(ridge length) segment records
-    crosses PCIe."""
-    cell, ka, kb, pts = eng.contour_segments(z_dev, mask_dev, x, y, level)
-    return link_segments(cell, ka, kb, pts)
+    """Device case analysis (csrc/contour.cu) + host linking (csrc/link.cu).  ``z_dev`` /
+    ``mask_dev`` are the device tensors of the (masked) field; nothing but the O(ridge length)
+    segment records crosses PCIe."""
+    return contour_lines_finish(eng, eng.contour_launch(z_dev, mask_dev, x, y, level))
+
+
+def contour_lines_finish(eng, handle):
+    """Second half of ``zero_contour_lines_device`` for callers that enqueue more device work
+    between the launch (``Engine.contour_launch``) and the linking."""
+    cell, ka, kb, pts = eng.contour_fetch(handle)
+    return link_segments_native(cell, ka, kb, pts, len(handle["x"]), len(handle["y"]))

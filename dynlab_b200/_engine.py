@@ -225,31 +225,63 @@ class Engine:
         return dd, conc, mask
 
     # -- contour segments -------------------------------------------------------------
+    _contour_cap = 0  # largest segment count seen so far (+ head room): avoids re-launches
+
+    def contour_launch(self, z, mask, x, y, level=0.0, cap=None):
+        """Enqueue the device pass of the contour extraction on the current stream; returns a
+        handle for ``contour_fetch``.  Nothing is synchronised."""
+        xdim, ydim = len(x), len(y)
+        with torch.cuda.device(self.device):
+            ws, wsz = self.workspace(xdim, ydim)
+            cap = int(cap or max(1 << 16, 8 * (xdim + ydim), self._contour_cap))
+            count = torch.zeros(1, dtype=torch.int64, device=self.device)
+            cell = self.empty(cap, dtype=torch.int64)
+            ka, kb = self.empty(cap, dtype=torch.int64), self.empty(cap, dtype=torch.int64)
+            pts = self.empty(cap, 4)
+            with self._timed("contour_segments"):
+                nat.check(nat.lib.dlb_contour_segments(
+                    z.data_ptr(), mask.data_ptr() if mask is not None else None, nat.dptr(x),
+                    xdim, nat.dptr(y), ydim, float(level), cell.data_ptr(), ka.data_ptr(),
+                    kb.data_ptr(), pts.data_ptr(), cap, count.data_ptr(), ws, wsz,
+                    self.stream()))
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(self.device))
+        return dict(z=z, mask=mask, x=x, y=y, level=level, cap=cap, count=count, cell=cell,
+                    ka=ka, kb=kb, pts=pts, done=done)
+
+    def contour_fetch(self, h):
+        """Host arrays (cell, key_a, key_b, pts[n, 4]) of a ``contour_launch``.  The records are
+        read on the copy stream, so kernels enqueued on the main stream after the launch (the
+        next slice of a sweep) keep running."""
+        with torch.cuda.device(self.device):
+            cs = self.copy_stream
+            cs.wait_event(h["done"])
+            with torch.cuda.stream(cs):
+                n_host = torch.empty(1, dtype=torch.int64, pin_memory=True)
+                h["count"].record_stream(cs)
+                n_host.copy_(h["count"], non_blocking=True)
+                cs.synchronize()
+                n = int(n_host[0])
+                if n > h["cap"]:  # did not fit: run again with room (on the main stream)
+                    Engine._contour_cap = n + n // 4
+                    return self.contour_fetch(self.contour_launch(
+                        h["z"], h["mask"], h["x"], h["y"], h["level"], cap=n + n // 8))
+                Engine._contour_cap = max(Engine._contour_cap, n + n // 4)
+                out = []
+                for key in ("cell", "ka", "kb", "pts"):
+                    t = h[key][:n]
+                    t.record_stream(cs)
+                    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=n > 4096)
+                    host.copy_(t, non_blocking=True)
+                    out.append(host)
+                cs.synchronize()
+        return tuple(t.numpy() for t in out)
+
     def contour_segments(self, z, mask, x, y, level=0.0):
         """Device pass of the contour extraction: returns host arrays (cell, key_a, key_b,
         pts[n, 4]) of the segments of the ``level`` contour of ``z`` (device tensor [ydim, xdim];
         ``mask`` uint8 device tensor or None)."""
-        xdim, ydim = len(x), len(y)
-        with torch.cuda.device(self.device):
-            ws, wsz = self.workspace(xdim, ydim)
-            cap = max(1 << 16, 8 * (xdim + ydim))
-            count = torch.zeros(1, dtype=torch.int64, device=self.device)
-            while True:
-                cell = self.empty(cap, dtype=torch.int64)
-                ka, kb = self.empty(cap, dtype=torch.int64), self.empty(cap, dtype=torch.int64)
-                pts = self.empty(cap, 4)
-                with self._timed("contour_segments"):
-                    nat.check(nat.lib.dlb_contour_segments(
-                        z.data_ptr(), mask.data_ptr() if mask is not None else None, nat.dptr(x),
-                        xdim, nat.dptr(y), ydim, float(level), cell.data_ptr(), ka.data_ptr(),
-                        kb.data_ptr(), pts.data_ptr(), cap, count.data_ptr(), ws, wsz,
-                        self.stream()))
-                n = int(count.item())
-                if n <= cap:
-                    break
-                cap = n + n // 8
-        return (cell[:n].cpu().numpy(), ka[:n].cpu().numpy(), kb[:n].cpu().numpy(),
-                pts[:n].cpu().numpy())
+        return self.contour_fetch(self.contour_launch(z, mask, x, y, level))
 
     # -- percentile -------------------------------------------------------------------
     def percentile(self, values, q):

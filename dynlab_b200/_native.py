@@ -41,6 +41,7 @@ SIGNATURES = {
                              _sz, _vp]),
     "dlb_contour_segments": (_i, [_vp, _vp, _dp, _i64, _dp, _i64, _d, _vp, _vp, _vp, _vp, _i64, _vp,
                                   _vp, _sz, _vp]),
+    "dlb_link_segments": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "dlb_select_scratch_bytes": (_sz, []),
     "dlb_order_statistics": (_i, [_vp, _i64, C.POINTER(C.c_int64), _i, _vp, _vp, _vp, _sz, _vp]),
     "dlb_dfma_peak": (_i, [_i, _dp, _dp]),

@@ -14,7 +14,7 @@ import torch.distributed as dist
 
 from . import _native as nat
 from . import sharding
-from ._contour import zero_contour_lines_device
+from ._contour import contour_lines_finish
 from ._engine import Engine, as_coord
 from ._resolve import resolve_flow
 from .utils import ODEINT_DEFAULT_TOL, parse_integrator_kwargs
@@ -46,6 +46,13 @@ def ftle_time_sweep(x, y, f, t_spans, edge_order: int = 1, percentile=None, ridg
     ydim, xdim = len(ys), len(xs)
     out = {}
     fm = eng.empty(ydim, xdim, 2)
+    pending = None  # (slice, contour handle, device results): linked while the next slice integrates
+
+    def finish(p):
+        k, handle, field, dd, mask = p
+        lines = contour_lines_finish(eng, handle)
+        out[k] = (field, dd, lines) if to_host else (field, dd, mask, lines)
+
     for k, span in enumerate(t_spans):
         if k % size != rank:
             continue
@@ -54,6 +61,9 @@ def ftle_time_sweep(x, y, f, t_spans, edge_order: int = 1, percentile=None, ridg
         t0, tf = float(span[0]), float(span[1])
         eng.flow_map(fid, params, xs, ys, 0, ydim, t0, tf, kw["rtol"], float(kw["atol"]),
                      kw["max_step"], kw["first_step"] or 0.0, out=fm)
+        if pending is not None:  # host linking of the previous slice overlaps this slice's K1
+            finish(pending)
+            pending = None
         xi_mode = nat.XI_LAPACK if ridge else nat.XI_NONE
         field, xi = eng.ftle_stencil(fm, 0, xs, ys, edge_order, abs(tf - t0), 0, ydim, xi_mode)
         if not ridge:
@@ -64,11 +74,11 @@ def ftle_time_sweep(x, y, f, t_spans, edge_order: int = 1, percentile=None, ridg
             # R:_base_classes.py:266-268 — np.percentile of the (unmasked) field values
             thr = eng.percentile(field, percentile)
         dd, conc, mask = eng.ridge_field(field, xi, xs, ys, edge_order, thr)
-        lines = zero_contour_lines_device(eng, dd, mask, xs, ys)
+        handle = eng.contour_launch(dd, mask, xs, ys)
         if to_host:
-            out[k] = (np.ma.MaskedArray(eng.to_host(field)),
-                      np.ma.MaskedArray(eng.to_host(dd), mask=eng.to_host(mask).astype(bool)),
-                      lines)
-        else:
-            out[k] = (field, dd, mask, lines)
+            field = np.ma.MaskedArray(eng.to_host(field))
+            dd = np.ma.MaskedArray(eng.to_host(dd), mask=eng.to_host(mask).astype(bool))
+        pending = (k, handle, field, dd, mask)
+    if pending is not None:
+        finish(pending)
     return out

@@ -193,6 +193,17 @@ int dlb_contour_segments(const double* d_z, const uint8_t* d_mask, const double*
                          uint64_t* d_count, void* d_workspace, size_t workspace_bytes,
                          void* stream);
 
+/* Polyline linking (host side) — chains the records of dlb_contour_segments
+ * (copied to the host) into the polylines `contour_generator(...).lines(level)` returns
+ * (R:src/dynlab/diagnostics/_base_classes.py:270): lines in the scan order of the cell they start
+ * in, open lines from where nothing leads in, closed loops repeating their first vertex.  Pure
+ * host code, O(n) apart from small per-row sorts; xdim, ydim: the grid the keys refer to.
+ * h_line_start [n + 1] and h_vertices [2 n][2] are caller-allocated;
+ * line l is h_vertices[h_line_start[l] .. h_line_start[l + 1]) as (x, y) pairs. */
+int dlb_link_segments(const int64_t* h_cell, const int64_t* h_key_a, const int64_t* h_key_b,
+                      const double* h_pts, int64_t n, int64_t xdim, int64_t ydim,
+                      int64_t* h_line_start, double* h_vertices, int64_t* h_n_lines);
+
 /* Order statistics — the two neighbouring sorted values `np.percentile(field,
  * percentile)` interpolates between (R:src/dynlab/diagnostics/_base_classes.py:266-268), found on
  * the device by an 8-pass radix select instead of a full-field D2H copy + host partition.
