@@ -21,7 +21,7 @@
 //
 // dm::pow_m01(s) = s^(-1/10) = err^(-1/5) for s = err^2: the step-size controller's
 // `error_norm ** -0.2` (scipy/integrate/_ivp/rk.py:153,164) without the square root: MUFU
-// lg2/ex2 seed in FP32 refined by two Newton steps in FP64 (relative error < 1e-15).
+// lg2/ex2 seed in FP32 refined by one third-order series step in FP64 (relative error < 1e-15).
 // dm::rcp(x): MUFU.RCP64H seed + two Newton steps, for the error-norm scaling.
 #pragma once
 #include <cuda_runtime.h>
@@ -274,16 +274,26 @@ __device__ __forceinline__ double rcp(double x) {
 
 // s^(-1/10) for s in [1e-12, 1e8]  (= err^(-1/5) for err = sqrt(s) in [1e-6, 1e4]).
 __device__ __forceinline__ double pow_m01(double s) {
-  double r = (double)exp2f(-0.1f * __log2f((float)s));  // ~1e-6 relative
-  // Newton on g(r) = r^-10 - s:  r <- r * (11 - s r^10) / 10   (error -> 5.5 e^2 per step)
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const double r2 = r * r;
-    const double r4 = r2 * r2;
-    const double r10 = r4 * r4 * r2;
-    r = r * (fma(-s, r10, 11.0) * 0.1);
-  }
-  return r;
+  // FP32 seed through the MUFU lg2 / ex2 units (.ftz: s is far from the subnormal range, so the
+  // scaling fix-ups of the IEEE-compliant forms are dead weight): ~1e-6 relative
+  float lg, sd;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"((float)s));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(-0.1f * lg));
+  const double r = (double)sd;
+  // with e = 1 - s r^10 (|e| ~ 1e-5):  s^(-1/10) = r (1 - e)^(-1/10)
+  //   = r (1 + e/10 + 11 e^2/200 + 77 e^3/2000 + O(e^4)),  remainder < 1e-20
+  const double r2 = r * r;
+  const double r4 = r2 * r2;
+  const double r10 = r4 * r4 * r2;
+  const double e = fma(-s, r10, 1.0);
+  const double p = fma(fma(0.0385, e, 0.055), e, 0.1);
+  return fma(r, e * p, r);
 }
+
+// max / min by one compare and a select.  fmax / fmin compile to DSETP.MAX plus five integer
+// instructions of NaN bookkeeping; on this kernel every issue slot next to the FP64 pipe counts.
+// NaN behaviour: a NaN in `b` is returned, a NaN in `a` is dropped.
+__device__ __forceinline__ double max_sel(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double min_sel(double a, double b) { return a < b ? a : b; }
 
 }  // namespace dm

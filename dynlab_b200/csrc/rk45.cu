@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(RK_BLOCK, DLB_RK_MINBLOCKS) rk45_kernel(const 
         double ssum = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          const double sc = P.atol[i] + fmax(fabs(y[i]), fabs(yn[i])) * rtol;
+          const double sc = P.atol[i] + dm::max_sel(fabs(y[i]), fabs(yn[i])) * rtol;
           const double ee =
               fma(K[5][i], E6,
                   fma(K[4][i], E5,
@@ -374,11 +374,11 @@ __global__ void __launch_bounds__(RK_BLOCK, DLB_RK_MINBLOCKS) rk45_kernel(const 
         // [1e-12, 1e8] (error_norm in [1e-6, 1e4]): outside it MAX_FACTOR / MIN_FACTOR win, so
         // the result is unchanged; a NaN norm maps to MIN_FACTOR like Python's max().
         double sc2 = (s < 1e8) ? s : 1e8;
-        sc2 = fmax(sc2, 1e-12);
+        sc2 = dm::max_sel(sc2, 1e-12);
         const double pw = 0.9 * dm::pow_m01(sc2);
         if (s < 1.0) {
-          double factor = (s == 0.0) ? 10.0 : fmin(10.0, pw);
-          if (rejected) factor = fmin(1.0, factor);
+          double factor = (s == 0.0) ? 10.0 : dm::min_sel(pw, 10.0);
+          if (rejected) factor = dm::min_sel(factor, 1.0);
           h_abs *= factor;
           t = t_new;
 #pragma unroll
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(RK_BLOCK, DLB_RK_MINBLOCKS) rk45_kernel(const 
           c_acc += 1;
           if (dir * (t - tf) >= 0) finish(0);  // base.py:207-208
         } else {
-          h_abs *= fmax(0.2, pw);
+          h_abs *= dm::max_sel(pw, 0.2);
           rejected = true;
           c_rej += 1;
         }
