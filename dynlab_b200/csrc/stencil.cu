@@ -73,6 +73,31 @@ enum { KIND_FTLE = 0, KIND_EULER = 1 };
 
 // ---- symmetric 2x2 eigen helpers ----
 
+// Reciprocal / square root / reciprocal square root from the MUFU seeds plus Newton steps in
+// FP64 (1-2 ulp), no special-case branches.  Arguments are positive and normal here.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));  // MUFU.RCP64H, ~20 bits
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+// g ~ sqrt(x), r ~ 1/sqrt(x): coupled (Goldschmidt) iteration, final residual step on each
+__device__ __forceinline__ void fast_sqrt_rsqrt(double x, double* g_out, double* r_out) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double g = x * r, h = 0.5 * r;
+  double e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  *g_out = fma(fma(-g, g, x), h, g);
+  *r_out = h + h;
+}
+
 // Eigenpair with the ordering and eigenvector sign np.linalg.eig (LAPACK dgeev: dlahqr's
 // deflation test + dlanv2's standardisation) produces for a symmetric 2x2 matrix, followed by
 // the reference's argsort selection (R:lagrangian.py:150-152, R:eulerian.py:327-330).
@@ -97,16 +122,29 @@ __device__ __forceinline__ void eig_sym_lapack(double a, double b, double d, boo
     cs = 1.0;
     sn = 0.0;
   } else {  // dlanv2 with c == b: always the real-eigenvalue branch
+    // LAPACK:  p = (a-d)/2, scale = max(|p|, |b|), z = p/scale*p + |b|/scale*|b|,
+    //          z = p + sign(sqrt(scale)*sqrt(z), p), w0 = d + z, w1 = d - |b|/z*|b|,
+    //          tau = dlapy2(b, z), cs = z/tau, sn = b/tau.
+    // Same quantities with reciprocals and one sqrt / one rsqrt from the MUFU seeds (the five
+    // IEEE divisions, two sqrt and the hypot of the literal transcription made this epilogue,
+    // not HBM, the bound of the Xi kernels): sqrt(scale)*sqrt(z) = scale*sqrt((p/scale)^2 +
+    // (b/scale)^2), |z| >= |b| > 0, tau = |z| sqrt(1 + (b/z)^2).  Within 2 ulp of LAPACK; the
+    // signs (of p, b, z) that fix the eigenvector orientation are untouched.
     const double p = 0.5 * (a - d);
-    const double bcmax = fabs(b), bcmis = fabs(b);
-    const double sc = fmax(fabs(p), bcmax);
-    double z = p / sc * p + bcmax / sc * bcmis;
-    z = p + copysign(sqrt(sc) * sqrt(z), p);
+    const double ab = fabs(b), ap = fabs(p);
+    const double sc = (ap > ab) ? ap : ab;
+    const double rs = fast_rcp(sc);
+    const double ps = p * rs, bs = ab * rs;
+    double g, r;
+    fast_sqrt_rsqrt(fma(ps, ps, bs * bs), &g, &r);
+    const double z = p + copysign(sc * g, p);
+    const double rz = fast_rcp(z);
     w0 = d + z;
-    w1 = d - bcmax / z * bcmis;
-    const double tau = hypot(b, z);
-    cs = z / tau;
-    sn = b / tau;
+    w1 = d - (ab * rz) * ab;
+    const double t = b * rz;
+    fast_sqrt_rsqrt(fma(t, t, 1.0), &g, &r);
+    cs = copysign(r, z);
+    sn = t * cs;
   }
   // eigenvectors: column 0 = (cs, sn) for w0, column 1 = (-sn, cs) for w1.
   // argsort ascending: idx[-1] is 0 only if w0 > w1; idx[0] is 1 only if w0 > w1.
@@ -599,8 +637,11 @@ struct RingSoA {
   }
 };
 
+#ifndef DLB_TB_MINB_XI
+#define DLB_TB_MINB_XI 6  // the eigenvector epilogue (dlanv2 path) needs more registers
+#endif
 template <int KIND, int MODE, bool XI, bool UX, bool UY, class Loader, class Ring>
-__global__ void __launch_bounds__(TB_THREADS, 8)
+__global__ void __launch_bounds__(TB_THREADS, XI ? DLB_TB_MINB_XI : 8)
     stencil_bulk_kernel(const StencilParams P, const Loader ld) {
   __shared__ __align__(128) double ring[TB_SLOTS][2 * TB_THREADS];
   __shared__ __align__(8) unsigned long long full[TB_SLOTS];
@@ -792,7 +833,7 @@ int launch_stencil(const StencilParams& P, const Loader& ld, cudaStream_t stream
   if (r_hi > r_lo && xdim > 2) {
     constexpr bool aos = std::is_same<Loader, LoaderAoS>::value;
     using Ring = typename std::conditional<aos, RingAoS, RingSoA>::type;
-    const bool bulk_ok = !XI && env_flag("DLB_STENCIL_BULK", 1) && (aos || (xdim % 2 == 0)) &&
+    const bool bulk_ok = env_flag("DLB_STENCIL_BULK", 1) && (aos || (xdim % 2 == 0)) &&
                          ld.aligned16();
     if (bulk_ok) {
       const long long nstrips = (xdim - 2 + TB_OUT - 1) / TB_OUT;
@@ -801,13 +842,13 @@ int launch_stencil(const StencilParams& P, const Loader& ld, cudaStream_t stream
       if (blocks > cap) blocks = cap;
       const unsigned g = (unsigned)blocks;
       if (P.ax.uniform && P.ay.uniform)
-        stencil_bulk_kernel<KIND, MODE, false, true, true, Loader, Ring><<<g, TB_THREADS, 0, stream>>>(P, ld);
+        stencil_bulk_kernel<KIND, MODE, XI, true, true, Loader, Ring><<<g, TB_THREADS, 0, stream>>>(P, ld);
       else if (P.ax.uniform)
-        stencil_bulk_kernel<KIND, MODE, false, true, false, Loader, Ring><<<g, TB_THREADS, 0, stream>>>(P, ld);
+        stencil_bulk_kernel<KIND, MODE, XI, true, false, Loader, Ring><<<g, TB_THREADS, 0, stream>>>(P, ld);
       else if (P.ay.uniform)
-        stencil_bulk_kernel<KIND, MODE, false, false, true, Loader, Ring><<<g, TB_THREADS, 0, stream>>>(P, ld);
+        stencil_bulk_kernel<KIND, MODE, XI, false, true, Loader, Ring><<<g, TB_THREADS, 0, stream>>>(P, ld);
       else
-        stencil_bulk_kernel<KIND, MODE, false, false, false, Loader, Ring><<<g, TB_THREADS, 0, stream>>>(P, ld);
+        stencil_bulk_kernel<KIND, MODE, XI, false, false, Loader, Ring><<<g, TB_THREADS, 0, stream>>>(P, ld);
       DLB_CUDA_CHECK(cudaGetLastError());
       return DLB_OK;
     }
