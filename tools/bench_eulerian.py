@@ -39,10 +39,19 @@ for name, mode, xi, b in (("attraction_rate(s_min)", nat.EULER_S_MIN, 0, 24), ("
 uh, vh = u.cpu().numpy(), v.cpu().numpy()
 d = AttractionRate()
 d.compute(x, y, u=uh, v=vh, edge_order=2)
+t0 = time.perf_counter(); d.compute(x, y, u=uh, v=vh, edge_order=2); e2e_uv_second = time.perf_counter() - t0
+d.compute(x, y, u=uh, v=vh, edge_order=2)
 t0 = time.perf_counter(); d.compute(x, y, u=uh, v=vh, edge_order=2); e2e_uv = time.perf_counter() - t0
 d.compute(x, y, f=flows.bickley_jet, t=0.0, edge_order=2)
 t0 = time.perf_counter(); d.compute(x, y, f=flows.bickley_jet, t=0.0, edge_order=2); e2e_ft = time.perf_counter() - t0
-res["e2e"] = {"u_v_host_arrays_ms": e2e_uv * 1e3, "h2d_bytes": 2 * 8 * N * N, "d2h_bytes": 8 * N * N,
+Engine.PINNED_RESULTS = True  # steady state of a loop over many fields (pinned result blocks cached)
+for _ in range(3): d.compute(x, y, u=uh, v=vh, edge_order=2)
+t0 = time.perf_counter(); d.compute(x, y, u=uh, v=vh, edge_order=2); e2e_uv_pinned = time.perf_counter() - t0
+for _ in range(3): d.compute(x, y, f=flows.bickley_jet, t=0.0, edge_order=2)
+t0 = time.perf_counter(); d.compute(x, y, f=flows.bickley_jet, t=0.0, edge_order=2); e2e_ft_pinned = time.perf_counter() - t0
+Engine.PINNED_RESULTS = False
+res["e2e"] = {"pinned_results_steady_state_ms": {"u_v_host_arrays": e2e_uv_pinned * 1e3, "f_t_route": e2e_ft_pinned * 1e3},
+              "u_v_host_arrays_ms": e2e_uv * 1e3, "u_v_host_arrays_second_call_ms": e2e_uv_second * 1e3, "h2d_bytes": 2 * 8 * N * N, "d2h_bytes": 8 * N * N,
               "f_t_route_ms": e2e_ft * 1e3, "points_per_s_u_v": N * N / e2e_uv, "points_per_s_f_t": N * N / e2e_ft}
 # CPU baseline: the reference's per-point loop (oracle port, single-threaded like the reference class) on a crop
 c = 384
