@@ -303,6 +303,26 @@ class Engine:
         return out, mask, xi
 
     # -- K0 ---------------------------------------------------------------------------
+    def euler_stencil_flow(self, mode, flow_id, params, t, x, y, edge_order, out_row0, out_rows,
+                           negate=False, xi_mode=nat.XI_NONE):
+        """K0 fused into K3: the Eulerian field of an analytic flow at time ``t`` on
+        meshgrid(x, y) without materialising (u, v)."""
+        xdim, ydim = len(x), len(y)
+        with torch.cuda.device(self.device):
+            out = self.empty(out_rows, xdim)
+            need_mask = mode in (nat.EULER_RATE, nat.EULER_RATIO)
+            mask = self.empty(out_rows, xdim, dtype=torch.uint8) if need_mask else None
+            xi = self.empty(out_rows, xdim, 2) if xi_mode != nat.XI_NONE else None
+            ws, wsz = self.workspace(xdim, ydim)
+            p = nat.darray(params)
+            with self._timed("euler_stencil_flow", 2):
+              nat.check(nat.lib.dlb_euler_stencil_flow(
+                mode, flow_id, p, len(params), float(t), nat.dptr(x), xdim, nat.dptr(y), ydim,
+                int(edge_order), out_row0, out_rows, int(bool(negate)), out.data_ptr(),
+                mask.data_ptr() if mask is not None else None,
+                xi.data_ptr() if xi is not None else None, xi_mode, ws, wsz, self.stream()))
+        return out, mask, xi
+
     def flow_eval_grid(self, flow_id, params, t, x, y):
         xdim, ydim = len(x), len(y)
         with torch.cuda.device(self.device):

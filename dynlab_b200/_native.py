@@ -37,6 +37,8 @@ SIGNATURES = {
                               _i, _vp, _sz, _vp]),
     "dlb_euler_stencil": (_i, [_i, _vp, _vp, _i64, _i64, _dp, _i64, _dp, _i64, _i, _i64, _i64, _i,
                                _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "dlb_euler_stencil_flow": (_i, [_i, _i, _dp, _i, _d, _dp, _i64, _dp, _i64, _i, _i64, _i64, _i,
+                                    _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "dlb_ridge_field": (_i, [_vp, _vp, _dp, _i64, _dp, _i64, _i, _i, _d, _vp, _vp, _vp, _vp, _vp,
                              _sz, _vp]),
     "dlb_contour_segments": (_i, [_vp, _vp, _dp, _i64, _dp, _i64, _d, _vp, _vp, _vp, _vp, _i64, _vp,

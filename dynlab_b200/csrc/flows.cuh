@@ -134,7 +134,94 @@ __device__ __forceinline__ void flow_time(const FlowConsts& fc, Trig& trig, cons
   }
 }
 
-// Space part.  Y/out have k_flow_info[ID].dim entries.
+// ---- x / y separation (grid evaluation) --------------------------------------------------------
+// On meshgrid(x, y) at a fixed time some flows factor into functions of x only and of y only
+// (double gyre: sin(pi f(x)) * cos(pi y); Bickley jet: sech^2(y/L) * cos(k (x - c t))).  The
+// fused flow + stencil kernels (eulerflow.cu) evaluate the x part once per column and the y part
+// once per row of a tile and only *combine* them per node - the transcendentals leave the
+// per-node cost.  FlowXY<ID>::NX / NY doubles per column / row; NX == 0: not separable, the
+// node is evaluated by flow_space.  combine() performs exactly the operations flow_space does
+// on the same intermediate values, so both give bit-identical velocities.
+template <int ID>
+struct FlowXY {
+  static constexpr int NX = 0, NY = 0;
+};
+template <>
+struct FlowXY<DLB_FLOW_DOUBLE_GYRE> {
+  static constexpr int NX = 3, NY = 2;  // (c3 sin(pi f), c4 cos(pi f), dfdx) | (sin, cos)(pi y)
+};
+template <>
+struct FlowXY<DLB_FLOW_AUTONOMOUS_DOUBLE_GYRE> {
+  static constexpr int NX = 2, NY = 2;  // (-pi sin(pi x), pi cos(pi x)) | (sin, cos)(pi y)
+};
+template <>
+struct FlowXY<DLB_FLOW_BICKLEY_JET> {
+  static constexpr int NX = 4, NY = 5;  // (s3, c3, s2, c2) | sech^2, tanh products
+};
+
+template <int ID, class Trig>
+__device__ __forceinline__ void flow_xpart(const FlowConsts& fc, Trig& trig, const double* tc,
+                                           double x, double* xp) {
+  const double* c = fc.c;
+  if constexpr (ID == DLB_FLOW_DOUBLE_GYRE) {
+    const double s = tc[0];  // sin(w t)
+    const double a = c[1] * s;
+    const double b = fma(-c[2], s, 1.0);
+    const double f = x * fma(a, x, b);
+    double sf, cf;
+    trig.sincos(DLB_PI * f, &sf, &cf);
+    xp[0] = c[3] * sf;
+    xp[1] = c[4] * cf;
+    xp[2] = fma(2 * a, x, b);
+  } else if constexpr (ID == DLB_FLOW_AUTONOMOUS_DOUBLE_GYRE) {
+    double sx, cx;
+    trig.sincos(DLB_PI * x, &sx, &cx);
+    xp[0] = -DLB_PI * sx;
+    xp[1] = DLB_PI * cx;
+  } else if constexpr (ID == DLB_FLOW_BICKLEY_JET) {
+    const double t = tc[0];
+    trig.sincos(c[5] * fma(-c[3], t, x), &xp[0], &xp[1]);
+    trig.sincos(c[4] * fma(-c[2], t, x), &xp[2], &xp[3]);
+  }
+}
+
+template <int ID, class Trig>
+__device__ __forceinline__ void flow_ypart(const FlowConsts& fc, Trig& trig, const double* tc,
+                                           double y, double* yp) {
+  const double* c = fc.c;
+  if constexpr (ID == DLB_FLOW_DOUBLE_GYRE || ID == DLB_FLOW_AUTONOMOUS_DOUBLE_GYRE) {
+    trig.sincos(y * DLB_PI, &yp[0], &yp[1]);
+  } else if constexpr (ID == DLB_FLOW_BICKLEY_JET) {
+    const double yl = y / c[1];
+    const double ch = 1 / cosh(yl);
+    const double sech2 = ch * ch, th = tanh(yl);
+    yp[0] = c[0] * sech2;
+    yp[1] = c[6] * th * sech2;
+    yp[2] = c[7] * th * sech2;
+    yp[3] = c[8] * sech2;
+    yp[4] = c[9] * sech2;
+  }
+}
+
+template <int ID>
+__device__ __forceinline__ void flow_combine(const double* xp, const double* yp, double* out) {
+  if constexpr (ID == DLB_FLOW_DOUBLE_GYRE) {
+    out[0] = xp[0] * yp[1];            // c3 sf cy
+    out[1] = xp[1] * yp[0] * xp[2];    // c4 cf sy dfdx
+  } else if constexpr (ID == DLB_FLOW_AUTONOMOUS_DOUBLE_GYRE) {
+    out[0] = xp[0] * yp[1];
+    out[1] = xp[1] * yp[0];
+  } else if constexpr (ID == DLB_FLOW_BICKLEY_JET) {
+    // U0 sech2 + 2 A3 U0 tanh sech2 cos(k3 ..) + 2 A2 U0 tanh sech2 cos(k2 ..)   (flows.py:94)
+    out[0] = fma(yp[2], xp[3], fma(yp[1], xp[1], yp[0]));
+    // -k3 A3 L U0 sech2 sin(k3 ..) - k2 A2 L U0 sech2 sin(k2 ..)                 (flows.py:95)
+    out[1] = fma(-yp[4], xp[2], yp[3] * xp[0]);
+  }
+}
+
+// Space part.  Y/out have k_flow_info[ID].dim entries.  Every multiply-add is written as an
+// explicit fma(): nothing is left to the compiler's contraction heuristics, so each inlined copy
+// (K0, K1, the fused Eulerian kernels, loop prologue vs. loop body) rounds identically.
 template <int ID, class Trig>
 __device__ __forceinline__ void flow_space(const FlowConsts& fc, Trig& trig, const double* tc,
                                            const double* Y, double* out) {
@@ -143,7 +230,7 @@ __device__ __forceinline__ void flow_space(const FlowConsts& fc, Trig& trig, con
   if constexpr (ID == DLB_FLOW_DOUBLE_GYRE) {
     const double s = tc[0];  // sin(w t)
     const double a = c[1] * s;
-    const double b = 1 - c[2] * s;
+    const double b = fma(-c[2], s, 1.0);
     const double f = x * fma(a, x, b);       // a x^2 + b x
     const double dfdx = fma(2 * a, x, b);    // 2 a x + b
     double sf, cf, sy, cy;
@@ -151,73 +238,69 @@ __device__ __forceinline__ void flow_space(const FlowConsts& fc, Trig& trig, con
     out[0] = c[3] * sf * cy;
     out[1] = c[4] * cf * sy * dfdx;
   } else if constexpr (ID == DLB_FLOW_AUTONOMOUS_DOUBLE_GYRE) {
-    double sx, cx, sy, cy;
-    trig.sincos2(DLB_PI * x, y * DLB_PI, &sx, &cx, &sy, &cy);
-    out[0] = -DLB_PI * sx * cy;
-    out[1] = DLB_PI * cx * sy;
+    double xp[2], yp[2];
+    flow_xpart<ID>(fc, trig, tc, x, xp);
+    flow_ypart<ID>(fc, trig, tc, y, yp);
+    flow_combine<ID>(xp, yp, out);
   } else if constexpr (ID == DLB_FLOW_BICKLEY_JET) {
-    const double t = tc[0];
-    const double yl = y / c[1];
-    const double ch = 1 / cosh(yl);
-    const double sech2 = ch * ch, th = tanh(yl);
-    double s3, c3, s2, c2;
-    trig.sincos2(c[5] * (x - c[3] * t), c[4] * (x - c[2] * t), &s3, &c3, &s2, &c2);
-    out[0] = c[0] * sech2 + c[6] * th * sech2 * c3 + c[7] * th * sech2 * c2;
-    out[1] = c[8] * sech2 * s3 - c[9] * sech2 * s2;
+    double xp[4], yp[5];
+    flow_xpart<ID>(fc, trig, tc, x, xp);
+    flow_ypart<ID>(fc, trig, tc, y, yp);
+    flow_combine<ID>(xp, yp, out);
   } else if constexpr (ID == DLB_FLOW_GLIDER) {
-    const double r = sqrt(x * x + y * y);
+    const double r = sqrt(fma(x, x, y * y));
     const double th2 = -2 * atan2(y, x);
     double s, cs;
     trig.sincos(th2, &s, &cs);
     s = 1.2 * s;
     cs = 1.4 - cs;
-    out[0] = r * (-y * s - cs * x);
-    out[1] = r * (x * s - cs * y) - 1;
+    out[0] = r * -fma(y, s, cs * x);
+    out[1] = fma(r, fma(x, s, -(cs * y)), -1.0);
   } else if constexpr (ID == DLB_FLOW_HILLS_VORTEX) {
     out[0] = 2.0 * x * y;
-    out[1] = -2.0 * (2.0 * x * x - 1.0) - 2.0 * y * y;
+    out[1] = fma(-2.0 * y, y, -2.0 * fma(2.0 * x, x, -1.0));
   } else if constexpr (ID == DLB_FLOW_SIGMOIDAL) {
-    out[0] = 0.4 * tanh(10.0 * (x - 0.5 * tc[0]));
+    out[0] = 0.4 * tanh(10.0 * fma(-0.5, tc[0], x));
     out[1] = y * 0;
   } else if constexpr (ID == DLB_FLOW_AUTONOMOUS_DUFFING) {
     out[0] = y;
-    out[1] = x - x * x * x;
+    out[1] = fma(-(x * x), x, x);
   } else if constexpr (ID == DLB_FLOW_DUFFING) {  // A, gamma, omega; tc = sin(omega t)
     out[0] = y;
-    out[1] = x - x * x * x - c[1] * y + c[0] * tc[0];
+    out[1] = fma(c[0], tc[0], fma(-c[1], y, fma(-(x * x), x, x)));
   } else if constexpr (ID == DLB_FLOW_PENDULUM) {  // A, gamma, omega; tc = sin(omega t)
     out[0] = y;
-    out[1] = -trig.sin(x) - c[1] * y + c[0] * tc[0];
+    out[1] = fma(c[0], tc[0], fma(-c[1], y, -trig.sin(x)));
   } else if constexpr (ID == DLB_FLOW_HURRICANE) {  // tc = cos(eye_omega t)
     const double yt = y - c[4];
-    const double den = x * x + yt * yt + c[0];
+    const double den = fma(yt, yt, x * x) + c[0];
     out[0] = -yt / den - c[3];
-    out[1] = x / den + c[2] * y * tc[0];
+    out[1] = fma(c[2] * y, tc[0], x / den);
   } else if constexpr (ID == DLB_FLOW_VAN_DER_POL) {  // A, mu, gamma, omega; tc = sin(omega t)
     out[0] = y;
-    out[1] = c[1] * (1 - x * x) * y - x - c[2] * y + c[0] * tc[0];
+    out[1] = fma(c[0], tc[0], fma(-c[2], y, fma(c[1] * fma(-x, x, 1.0), y, -x)));
   } else if constexpr (ID == DLB_FLOW_BEAD) {  // 1/epsilon, gamma
     double s, cs;
     trig.sincos(x, &s, &cs);
     out[0] = y;
-    out[1] = c[0] * (s * (c[1] * cs - 1) - y);
+    out[1] = c[0] * fma(s, fma(c[1], cs, -1.0), -y);
   } else if constexpr (ID == DLB_FLOW_LOTKA_VOLTERRA) {  // alpha, beta, gamma, delta
-    out[0] = c[0] * x - c[1] * x * y;
-    out[1] = c[3] * x * y - c[2] * y;
+    out[0] = fma(-(c[1] * x), y, c[0] * x);
+    out[1] = fma(c[3] * x, y, -(c[2] * y));
   } else if constexpr (ID == DLB_FLOW_ABC) {  // ABC_Amplitude, A, B, C; tc = sin(pi t)
     const double z = Y[2];
-    const double At = c[1] + c[0] * tc[0];
+    const double At = fma(c[0], tc[0], c[1]);
     double sx, cx, sy, cy, sz, cz;
     trig.sincos2(x, y, &sx, &cx, &sy, &cy);
     trig.sincos(z, &sz, &cz);
-    out[0] = At * sz + c[3] * cy;
-    out[1] = c[2] * sx + At * cz;
-    out[2] = c[3] * sy + c[2] * cx;
+    out[0] = fma(At, sz, c[3] * cy);
+    out[1] = fma(c[2], sx, At * cz);
+    out[2] = fma(c[3], sy, c[2] * cx);
   } else if constexpr (ID == DLB_FLOW_LORENZ) {  // sigma, rho, beta
     const double z = Y[2];
     out[0] = c[0] * (y - x);
-    out[1] = x * (c[1] - z) - y;
-    out[2] = x * y - c[2] * z;
+    out[1] = fma(x, c[1] - z, -y);
+    out[2] = fma(x, y, -(c[2] * z));
   }
 }
 

@@ -483,8 +483,9 @@ int fill_common(Rk45Params& P, int flow_id, const double* h_params, int n_params
 extern "C" size_t dlb_workspace_bytes(int64_t xdim, int64_t ydim) {
   if (xdim < 0) xdim = 0;
   if (ydim < 0) ydim = 0;
-  // x, y, 3 + 3 coefficient arrays, the interleaved y record (4 per row) and 32-byte slack
-  return 256 + sizeof(double) * (size_t)(4 * (xdim + ydim) + 4 * ydim + 64);
+  // x, y, 3 + 3 coefficient arrays, the interleaved y record (4 per row), the stencils' own
+  // cached copy of x and y, and 32-byte slack
+  return 256 + sizeof(double) * (size_t)(5 * (xdim + ydim) + 4 * ydim + 64);
 }
 
 extern "C" int dlb_flowmap_rk45(int flow_id, const double* h_params, int n_params,

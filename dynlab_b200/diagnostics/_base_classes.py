@@ -29,6 +29,27 @@ class UnsupportedIntegratorError(NotImplementedError):
     """``integrator=`` is not one of the device integrator sentinels."""
 
 
+class _Deferred:
+    """Device tensor that is only computed if somebody asks for it (``fn`` returns a tuple of
+    tensors, ``index`` selects one; the tuple is computed once and shared)."""
+
+    def __init__(self, fn, index, cache):
+        self.fn, self.index, self.cache = fn, index, cache
+
+    def resolve(self):
+        if "value" not in self.cache:
+            self.cache["value"] = self.fn()
+        return self.cache["value"][self.index]
+
+
+class _FlowSource:
+    """Stands for ``f(t, np.meshgrid(x, y))`` of a flow with a device twin: the Eulerian kernels
+    evaluate it on the fly (csrc/eulerflow.cu) instead of reading ``u, v`` arrays."""
+
+    def __init__(self, fid, params, t):
+        self.fid, self.params, self.t = fid, params, float(t)
+
+
 class _LazyHost:
     """Attribute that lives on the device until somebody reads it (then cached on the host)."""
 
@@ -43,11 +64,13 @@ class _LazyHost:
             dev = obj.__dict__.get(self.dev)
             if dev is None:
                 raise AttributeError(self.host[1:-5])
+            if isinstance(dev, _Deferred):
+                dev = obj.__dict__[self.dev] = dev.resolve()
             host = obj.__dict__[self.host] = Engine.get(dev.device).to_host(dev)
         return host
 
     def __set__(self, obj, value):
-        if isinstance(value, torch.Tensor) and value.is_cuda:
+        if isinstance(value, _Deferred) or (isinstance(value, torch.Tensor) and value.is_cuda):
             obj.__dict__[self.dev] = value
             obj.__dict__.pop(self.host, None)
         else:
@@ -120,8 +143,13 @@ class EulerianDiagnostic2D(Diagnostic2D, ABC):
             _, fid, dim, params = resolve_flow(f)
             if dim != 2:
                 raise ValueError("a 2-D diagnostic needs a 2-D flow")
-            ud, vd = eng.flow_eval_grid(fid, params, float(t), self._xf, self._yf)
-            self.u, self.v = ud, vd  # downloaded only if the user reads them
+            # K0 is fused into the stencil kernel: (u, v) are never written unless the user reads
+            # the attributes, in which case dlb_flow_eval_grid produces the same values
+            xf, yf, tt = self._xf, self._yf, float(t)
+            cache = {}
+            self.u = _Deferred(lambda: eng.flow_eval_grid(fid, params, tt, xf, yf), 0, cache)
+            self.v = _Deferred(lambda: eng.flow_eval_grid(fid, params, tt, xf, yf), 1, cache)
+            ud, vd = _FlowSource(fid, params, tt), None
         else:
             raise RuntimeError(
                 "Either a velocity field (u, v) or a function and timestep from which to "
@@ -134,12 +162,19 @@ class EulerianDiagnostic2D(Diagnostic2D, ABC):
         """Run K3 on the whole grid (row-sharded when a process group is active)."""
         eng = Engine.get()
         rank, size = sharding.world()
+        fused = isinstance(ud, _FlowSource)
         if size == 1:
+            if fused:
+                return eng.euler_stencil_flow(mode, ud.fid, ud.params, ud.t, self._xf, self._yf,
+                                              edge_order, 0, self.ydim, negate, xi_mode)
             return eng.euler_stencil(mode, ud, vd, 0, self._xf, self._yf, edge_order, 0,
                                      self.ydim, negate, xi_mode)
         slab = sharding.partition(self.ydim, size, rank)
         f = m = xi = None
-        if slab.rows:
+        if slab.rows and fused:
+            f, m, xi = eng.euler_stencil_flow(mode, ud.fid, ud.params, ud.t, self._xf, self._yf,
+                                              edge_order, slab.row0, slab.rows, negate, xi_mode)
+        elif slab.rows:
             f, m, xi = eng.euler_stencil(mode, ud[slab.lo:slab.hi], vd[slab.lo:slab.hi], slab.lo,
                                          self._xf, self._yf, edge_order, slab.row0, slab.rows,
                                          negate, xi_mode)

@@ -166,6 +166,20 @@ int dlb_euler_stencil(int mode, const double* d_u, const double* d_v, int64_t nl
                       double* d_field, uint8_t* d_mask, double* d_xi, int xi_mode,
                       void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* K0 fused into K3 ("8 B/pt when f, t is supplied and K0 is fused") — the same
+ * fields as dlb_euler_stencil for an analytic flow at time t on meshgrid(x, y)
+ * (R:src/dynlab/diagnostics/_base_classes.py:101-102 followed by R:eulerian.py:47-59 / :179-195 /
+ * :317-333) without writing or reading (u, v): the velocity of a node is produced in registers
+ * where the stencil consumes it (x / y separable flows: transcendentals once per column / row of
+ * a tile: double gyre, autonomous double gyre, Bickley jet).  Velocities are bit-identical to
+ * dlb_flow_eval_grid's, so the output equals dlb_flow_eval_grid + dlb_euler_stencil exactly.  Rows [out_row0, out_row0 + out_rows) of any
+ * rank's slab can be produced without a halo.  2-D flows only. */
+int dlb_euler_stencil_flow(int mode, int flow_id, const double* h_params, int n_params, double t,
+                           const double* h_x, int64_t xdim, const double* h_y, int64_t ydim,
+                           int edge_order, int64_t out_row0, int64_t out_rows, int negate,
+                           double* d_field, uint8_t* d_mask, double* d_xi, int xi_mode,
+                           void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* Ridge field — gradient + Hessian of a scalar field, directional derivative
  * grad(f).xi and concavity xi^T H xi, with the reference's masks (field <= 0, concavity >= 0,
  * field <= threshold when use_threshold).  Replaces RidgeExtractor2D.extract_ridges up to the

@@ -481,6 +481,62 @@ def test_no_out_of_bounds_writes(dl):
         os.environ.pop("DLB_STENCIL_BULK", None)
 
 
+def test_fused_flow_stencil_equals_two_kernel_path(dl):
+    """csrc/eulerflow.cu (K0 fused into K3, x/y-separable evaluation) is bit-identical to
+    dlb_flow_eval_grid + dlb_euler_stencil: every 2-D flow, all four modes, both eigenvector
+    modes, uniform and non-uniform axes, both edge orders, row slabs, tiny grids; and the lazily
+    evaluated ``u, v`` attributes of the public classes."""
+    from dynlab_b200 import _native as nat
+    from dynlab_b200._engine import Engine
+    from dynlab_b200.flows import FLOW_REGISTRY
+    from oracle import py_oracle as po
+
+    eng = Engine.get()
+    rng = np.random.default_rng(8)
+    grids = [(np.linspace(0.1, 1.9, 97), np.linspace(0.05, 0.95, 71)),
+             (np.sort(rng.uniform(0.1, 1.9, 64)), np.linspace(0.05, 0.95, 130)),
+             (np.linspace(0.1, 1.9, 33), np.sort(rng.uniform(0.05, 0.95, 67))),
+             (np.sort(rng.uniform(0.1, 1.9, 5)), np.sort(rng.uniform(0.05, 0.95, 3)))]
+    modes = [(nat.EULER_S_MIN, nat.XI_NONE), (nat.EULER_S_MAX, nat.XI_LAPACK),
+             (nat.EULER_S_MIN, nat.XI_FORCED), (nat.EULER_RATE, nat.XI_NONE),
+             (nat.EULER_RATIO, nat.XI_NONE)]
+    for name, (fid, dim, _) in FLOW_REGISTRY.items():
+        if dim != 2:
+            continue
+        params = po.flow_params(name)
+        scale = 1.0
+        if name == "bickley_jet":
+            scale = 1.0e4  # its natural length scale (Mm-sized jet)
+        for gi, (x0, y0) in enumerate(grids):
+            x, y = x0 * scale, (y0 - 0.5) * scale
+            ydim = len(y)
+            eo = 1 + gi % 2
+            u, v = eng.flow_eval_grid(fid, params, 0.37, x, y)
+            for mode, xim in modes:
+                neg = mode == nat.EULER_S_MIN and xim == nat.XI_FORCED
+                ref = eng.euler_stencil(mode, u, v, 0, x, y, eo, 0, ydim, neg, xim)
+                got = eng.euler_stencil_flow(mode, fid, params, 0.37, x, y, eo, 0, ydim, neg, xim)
+                for a, b in zip(ref, got):
+                    assert (a is None) == (b is None)
+                    if a is not None:  # bit for bit: flows.cuh leaves no contraction to the compiler
+                        assert torch.equal(a, b) or (a.dtype == torch.float64 and torch.equal(
+                            a.view(torch.int64), b.view(torch.int64))), (name, gi, mode, xim)
+                if ydim >= 8:  # a slab in the middle and the two boundary slabs
+                    for r0, rows in ((0, 3), (2, ydim - 5), (ydim - 2, 2)):
+                        part = eng.euler_stencil_flow(mode, fid, params, 0.37, x, y, eo, r0, rows, neg, xim)
+                        assert torch.equal(part[0].view(torch.int64), got[0][r0:r0 + rows].view(torch.int64))
+    # public API: f, t route == u, v route; u / v attributes appear on demand
+    x, y = np.linspace(0, 2, 201), np.linspace(0, 1, 101)
+    d = dl.diagnostics.TrajectoryRepulsionRate()
+    f1 = d.compute(x, y, f=dl.flows.double_gyre, t=0.3, edge_order=2)
+    assert "_u_host" not in d.__dict__
+    u, v = d.u, d.v
+    assert u.shape == (101, 201) and "_u_host" in d.__dict__
+    f2 = dl.diagnostics.TrajectoryRepulsionRate().compute(x, y, u=u, v=v, edge_order=2)
+    assert np.array_equal(np.ma.getdata(f1), np.ma.getdata(f2))
+    assert np.array_equal(np.ma.getmaskarray(f1), np.ma.getmaskarray(f2))
+
+
 def test_staged_host_to_device_copy(dl, monkeypatch):
     """Engine.to_device / to_host: the multi-threaded pinned-staging paths (large arrays) move
     exactly the bytes of the plain copy - ragged last chunk, fewer chunks than workers,

@@ -35,6 +35,14 @@ for name, mode, xi, b in (("attraction_rate(s_min)", nat.EULER_S_MIN, 0, 24), ("
     gbs = b * N * N / ms / 1e6
     res["kernels"][name] = {"ms": ms, "algorithmic_bytes_per_point": b, "GB_per_s": gbs, "frac_of_measured_hbm": gbs / hbm,
                             "points_per_s": N * N / ms * 1e3}
+# K0 fused into K3 (no u, v in HBM): algorithmic bytes = the 8 B/point result (+ mask / Xi)
+res["fused_flow_stencil"] = {}
+for name, mode, xi, b in (("attraction_rate(s_min)", nat.EULER_S_MIN, 0, 8), ("trajectory_repulsion_rate", nat.EULER_RATE, 0, 9),
+                          ("iles_eigen(s_min+Xi forced)", nat.EULER_S_MIN, 2, 24)):
+    ms = ev(lambda: eng.euler_stencil_flow(mode, fid, params, 0.0, x, y, 2, 0, N, False, xi))
+    res["fused_flow_stencil"][name] = {"ms": ms, "two_kernel_ms": k0 + res["kernels"][name]["ms"],
+                                       "algorithmic_bytes_per_point": b, "GB_per_s": b * N * N / ms / 1e6,
+                                       "points_per_s": N * N / ms * 1e3}
 # end to end through the public API
 uh, vh = u.cpu().numpy(), v.cpu().numpy()
 d = AttractionRate()
