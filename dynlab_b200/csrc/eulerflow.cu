@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(EF_BLOCK)
         d0dy = fma(ycz.x, D.x, fma(yab.y, C.x, yab.x * U.x));
         d1dy = fma(ycz.x, D.y, fma(yab.y, C.y, yab.x * U.y));
       }
-      if (emit_lane) emit<KIND_EULER, MODE, XI>(P, C, d0dx, d1dx, d0dy, d1dy, o);
+      emit_pred<KIND_EULER, MODE, XI>(P, C, d0dx, d1dx, d0dy, d1dy, o, nullptr, emit_lane);
       o += xdim;
       U = C;
       C = D;

@@ -26,6 +26,8 @@
 #include <type_traits>
 #include <vector>
 
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through the runtime
+
 #include "stencil_device.cuh"
 
 using dlbst::check_slab;
@@ -366,6 +368,235 @@ __global__ void __launch_bounds__(TB_THREADS, XI ? DLB_TB_MINB_XI : 8)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA tile variant (default).  The ncu captures of the bulk kernel above showed that it is not
+// the DRAM pipe that limits it but the issue slots: per 126-point row a CTA paid a barrier, an
+// mbarrier wait with run-time slot / parity arithmetic and, in warp 0, one or two 1-D bulk-copy
+// issues — 88 non-FP64 instructions per warp row against 31 FP64 (2 * FP64 + other = the measured
+// time).  Here the TMA engine moves whole [TM_RT rows x 128 columns] tiles with ONE
+// `cp.async.bulk.tensor.2d` per array (SASS: UTMALDG) described by a CUtensorMap, the pipeline
+// is counted in stages instead of rows (one mbarrier wait and one __syncthreads per 8 rows, all
+// shared-memory offsets inside a stage are compile-time constants because the row loop is fully
+// unrolled) and it runs across task boundaries, so a new task does not start with an empty pipe.
+// Out-of-range rows / columns of a tile are zero-filled by the TMA unit and never read back.
+constexpr int TM_THREADS = 128;                 // tile width = threads per CTA
+constexpr int TM_OUT = TM_THREADS - 2;          // output columns per tile
+#ifndef DLB_TM_RT
+#define DLB_TM_RT 4  // measured: 4 rows x 4 stages (32 KB, 6 CTAs/SM) best; 2..8 rows, 2..6 stages within 5 %
+#endif
+constexpr int TM_RT = DLB_TM_RT;                // rows per stage
+constexpr int TM_SPT = 64 / TM_RT;              // stages per task
+constexpr int TM_LOAD = TM_RT * TM_SPT;         // loaded rows per task (64)
+constexpr int TM_ROWS = TM_LOAD - 2;            // output rows per task (62)
+#ifndef DLB_TM_STAGES
+#define DLB_TM_STAGES 4
+#endif
+constexpr int TM_STAGES = DLB_TM_STAGES;        // stages in flight
+constexpr int TM_STAGE_BYTES = TM_RT * TM_THREADS * 16;
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(smem_u32(dst)),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int KIND, int MODE, bool XI, bool AOS>
+__global__ void __launch_bounds__(TM_THREADS)
+    stencil_tma_kernel(const StencilParams P, const __grid_constant__ CUtensorMap map0,
+                       const __grid_constant__ CUtensorMap map1) {
+  extern __shared__ __align__(128) unsigned char tiles[];  // [TM_STAGES][TM_STAGE_BYTES]
+  __shared__ __align__(8) unsigned long long full[TM_STAGES];
+  __shared__ double2 ysm[TM_ROWS][2];
+  __shared__ double2 logtab_s[KIND == KIND_FTLE ? 128 : 1];
+  const long long xdim = P.ax.n, ydim = P.ay.n;
+  const int t = threadIdx.x;
+  if (KIND == KIND_FTLE) logtab_s[t] = g_logtab[t];  // TM_THREADS == 128 entries
+  const long long r_lo = (P.out_row0 > 1) ? P.out_row0 : 1;
+  const long long r_hi = (P.out_row0 + P.out_rows < ydim - 1) ? P.out_row0 + P.out_rows : ydim - 1;
+  const long long ncols_out = xdim - 2;
+  if (r_hi <= r_lo || ncols_out <= 0) return;
+  const long long nstrips = (ncols_out + TM_OUT - 1) / TM_OUT;
+  const long long nchunks = (r_hi - r_lo + TM_ROWS - 1) / TM_ROWS;
+  const long long ntasks = nstrips * nchunks;
+  if ((long long)blockIdx.x >= ntasks) return;
+  const long long my_tasks = (ntasks - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const long long total_stages = my_tasks * TM_SPT;
+  const bool ux = P.ax.uniform != 0, uy = P.ay.uniform != 0;
+  const double ix = P.ax.inv2h, iy = P.ay.inv2h;
+
+  // producer side (thread 0): stage q of this CTA's stream = stage (q % TM_SPT) of its task q / TM_SPT
+  auto issue = [&](long long q) {
+    const long long task = blockIdx.x + (q / TM_SPT) * gridDim.x;
+    const int st = (int)(q % TM_SPT);
+    const long long chunk = task / nstrips, strip = task - chunk * nstrips;
+    const int c0 = (int)(strip * TM_OUT);
+    const int lrow = (int)(r_lo + chunk * TM_ROWS - 1 - P.grow0) + st * TM_RT;
+    const int slot = (int)(q % TM_STAGES);
+    unsigned char* dst = tiles + slot * TM_STAGE_BYTES;
+    mbar_expect_tx(&full[slot], TM_STAGE_BYTES);
+    if (AOS) {
+      tma_load_2d(dst, &map0, 2 * c0, lrow, &full[slot]);
+    } else {
+      tma_load_2d(dst, &map0, c0, lrow, &full[slot]);
+      tma_load_2d(dst + TM_STAGE_BYTES / 2, &map1, c0, lrow, &full[slot]);
+    }
+  };
+  if (t == 0) {
+#pragma unroll
+    for (int i = 0; i < TM_STAGES; ++i) mbar_init(&full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (long long q = 0; q < TM_STAGES && q < total_stages; ++q) issue(q);
+  }
+  __syncthreads();
+
+  long long q = 0;  // stages consumed so far (CTA-uniform)
+  for (long long it = 0; it < my_tasks; ++it) {
+    const long long task = blockIdx.x + it * gridDim.x;
+    const long long chunk = task / nstrips, strip = task - chunk * nstrips;
+    const long long c0 = strip * TM_OUT;
+    const long long g0 = r_lo + chunk * TM_ROWS;  // first output row of the task
+    const int nrows = (int)((g0 + TM_ROWS < r_hi) ? TM_ROWS : r_hi - g0);
+    const long long col = (c0 + t < xdim) ? c0 + t : xdim - 1;
+    const bool emit_thread = (t >= 1) && (t <= TM_OUT) && (c0 + t <= xdim - 2);
+    const int tl = (t > 0) ? t - 1 : 0, tr = (t < TM_THREADS - 1) ? t + 1 : TM_THREADS - 1;
+    double xa = 0.0, xb = 0.0, xc = 0.0;
+    if (!ux) {
+      xa = __ldg(P.ax.ca + col);
+      xb = __ldg(P.ax.cb + col);
+      xc = __ldg(P.ax.cc + col);
+    }
+    if (!uy) {
+      __syncthreads();  // the previous task's readers of ysm are done
+      if (t < nrows) {
+        const double2* src = P.ay4 + 2 * (g0 + t);
+        ysm[t][0] = __ldg(src);
+        ysm[t][1] = __ldg(src + 1);
+      }
+      __syncthreads();
+    }
+    // loaded row r of the task is global row g0 - 1 + r; while row r streams in as D, the centre
+    // row r - 1 (registers C, L, R) with U = row r - 2 is emitted: output row index k = r - 2
+    double2 U = make_double2(0.0, 0.0), C = U, L = U, R = U;
+    long long o = (g0 - 2 - P.out_row0) * xdim + col;  // output offset of k = -2 (never stored)
+#pragma unroll 1
+    for (int st = 0; st < TM_SPT; ++st, ++q) {
+      const int slot = (int)(q % TM_STAGES);
+      const unsigned parity = (unsigned)((q / TM_STAGES) & 1);
+      while (!mbar_try_wait(&full[slot], parity)) {
+      }
+      const unsigned char* tile = tiles + slot * TM_STAGE_BYTES;
+#pragma unroll
+      for (int j = 0; j < TM_RT; ++j) {
+        double2 D, Ld, Rd;
+        if (AOS) {
+          const double2* row = reinterpret_cast<const double2*>(tile) + j * TM_THREADS;
+          D = row[t];
+          Ld = row[tl];
+          Rd = row[tr];
+        } else {
+          const double* ru = reinterpret_cast<const double*>(tile) + j * TM_THREADS;
+          const double* rv = ru + TM_RT * TM_THREADS;
+          D = make_double2(ru[t], rv[t]);
+          Ld = make_double2(ru[tl], rv[tl]);
+          Rd = make_double2(ru[tr], rv[tr]);
+        }
+        const int k = st * TM_RT + j - 2;  // output row of the centre held in C
+        double d0dx, d1dx, d0dy, d1dy;
+        if (ux) {
+          d0dx = (R.x - L.x) * ix;
+          d1dx = (R.y - L.y) * ix;
+        } else {
+          d0dx = fma(xc, R.x, fma(xb, C.x, xa * L.x));
+          d1dx = fma(xc, R.y, fma(xb, C.y, xa * L.y));
+        }
+        if (uy) {
+          d0dy = (D.x - U.x) * iy;
+          d1dy = (D.y - U.y) * iy;
+        } else {
+          const int kc = (k < 0) ? 0 : k;
+          const double2 yab = ysm[kc][0], ycz = ysm[kc][1];
+          d0dy = fma(ycz.x, D.x, fma(yab.y, C.x, yab.x * U.x));
+          d1dy = fma(ycz.x, D.y, fma(yab.y, C.y, yab.x * U.y));
+        }
+        emit_pred<KIND, MODE, XI>(P, C, d0dx, d1dx, d0dy, d1dy, o,
+                                  KIND == KIND_FTLE ? logtab_s : nullptr,
+                                  emit_thread && k >= 0 && k < nrows);
+        o += xdim;
+        U = C;
+        C = D;
+        L = Ld;
+        R = Rd;
+      }
+      // every thread has read this stage: hand its slot back to the TMA unit
+      __syncthreads();
+      if (t == 0 && q + TM_STAGES < total_stages) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(q + TM_STAGES);
+      }
+    }
+  }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// 2-D FP64 tensor [rows][inner] with row pitch `pitch_bytes`, box [TM_RT][box_inner]
+bool make_tile_map(CUtensorMap* map, const void* base, long long inner, long long rows,
+                   long long pitch_bytes, int box_inner) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || ((uintptr_t)base & 15u) || (pitch_bytes & 15) || inner <= 0 || rows <= 0 ||
+      inner >= (1ll << 32) || rows >= (1ll << 32) || pitch_bytes >= (1ll << 40))
+    return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)pitch_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)TM_RT};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), gdim, gstride, box,
+            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int KIND, int MODE, bool XI, bool AOS>
+int launch_tma(const StencilParams& P, const CUtensorMap& m0, const CUtensorMap& m1,
+               long long ntasks, cudaStream_t stream) {
+  auto kern = stencil_tma_kernel<KIND, MODE, XI, AOS>;
+  constexpr int dyn = TM_STAGES * TM_STAGE_BYTES;
+  static bool configured = false;
+  static int per_sm = 1;
+  if (!configured) {
+    DLB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    DLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TM_THREADS, dyn));
+    if (per_sm < 1) per_sm = 1;
+    configured = true;
+  }
+  long long blocks = (long long)num_sms() * per_sm;
+  if (blocks > ntasks) blocks = ntasks;
+  kern<<<(unsigned)blocks, TM_THREADS, dyn, stream>>>(P, m0, m1);
+  DLB_CUDA_CHECK(cudaGetLastError());
+  return DLB_OK;
+}
+
 // (fl(1/c), -ln(fl(1/c))) for c = 1 + i/128, uploaded once per process and device.
 int ensure_logtab() {
   static std::mutex mu;
@@ -411,6 +642,21 @@ int launch_stencil(const StencilParams& P, const Loader& ld, cudaStream_t stream
     using Ring = typename std::conditional<aos, RingAoS, RingSoA>::type;
     const bool bulk_ok = env_flag("DLB_STENCIL_BULK", 1) && (aos || (xdim % 2 == 0)) &&
                          ld.aligned16();
+    if (bulk_ok && env_flag("DLB_STENCIL_TMA", 1)) {
+      CUtensorMap m0, m1;
+      bool ok;
+      if constexpr (aos) {
+        ok = make_tile_map(&m0, ld.p, 2 * xdim, P.nloc, 16 * xdim, 2 * TM_THREADS);
+        m1 = m0;
+      } else {
+        ok = make_tile_map(&m0, ld.u, xdim, P.nloc, 8 * xdim, TM_THREADS) &&
+             make_tile_map(&m1, ld.v, xdim, P.nloc, 8 * xdim, TM_THREADS);
+      }
+      if (ok) {
+        const long long ntasks = ((xdim - 2 + TM_OUT - 1) / TM_OUT) * ((r_hi - r_lo + TM_ROWS - 1) / TM_ROWS);
+        return launch_tma<KIND, MODE, XI, aos>(P, m0, m1, ntasks, stream);
+      }
+    }
     if (bulk_ok) {
       const long long nstrips = (xdim - 2 + TB_OUT - 1) / TB_OUT;
       const long long nchunks = (r_hi - r_lo + TB_ROWS - 1) / TB_ROWS;

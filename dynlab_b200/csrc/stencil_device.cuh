@@ -418,6 +418,42 @@ __device__ __forceinline__ void emit(const StencilParams& P, double2 C, double d
   }
 }
 
+// Same epilogue for the streaming interior kernels: everything is computed unconditionally and
+// only the stores are predicated, so a fully unrolled group of rows stays ONE basic block and
+// the scheduler can interleave the rows' dependent FP64 chains (with `if (lane emits) emit(...)`
+// every row was its own BSSY/BSYNC region; ncu: fixed-latency "wait" was the top stall).  The
+// eigenvector and rate / ratio variants keep their data-dependent branches (deflation test,
+// IEEE division) and go through emit().
+template <int KIND, int MODE, bool XI>
+__device__ __forceinline__ void emit_pred(const StencilParams& P, double2 C, double d0dx,
+                                          double d1dx, double d0dy, double d1dy, long long o,
+                                          const double2* logtab, bool store) {
+  if constexpr (KIND == KIND_FTLE && !XI) {
+    const double c11 = fma(d0dx, d0dx, d1dx * d1dx);
+    const double c12 = fma(d0dx, d0dy, d1dx * d1dy);
+    const double c22 = fma(d0dy, d0dy, d1dy * d1dy);
+    const double hm = 0.5 * (c11 - c22);
+    const double lam = 0.5 * (c11 + c22) + fast_sqrt(fma(hm, hm, c12 * c12));
+    double fl = fast_log_ge1_tab(lam, logtab);       // meaningless below 1, selected away
+    fl = (lam < CUDART_INF) ? fl : lam;              // inf -> inf, NaN -> NaN like np.log
+    const double out = (lam >= 1.0) ? P.scale * fl : ((lam != lam) ? lam : 0.0);
+    if (store) P.field[o] = out;
+  } else if constexpr (KIND == KIND_EULER && !XI &&
+                       (MODE == DLB_EULER_S_MIN || MODE == DLB_EULER_S_MAX)) {
+    const double a = d0dx, d = d1dy, b = 0.5 * (d0dy + d1dx);
+    const double hm = 0.5 * (a - d);
+    const double rad = fast_sqrt(fma(hm, hm, b * b));
+    double out = (MODE == DLB_EULER_S_MAX) ? 0.5 * (a + d) + rad : 0.5 * (a + d) - rad;
+    if (P.negate) out = -out;
+    if (store) {
+      P.field[o] = out;
+      if (P.mask) P.mask[o] = 0;
+    }
+  } else {
+    if (store) emit<KIND, MODE, XI>(P, C, d0dx, d1dx, d0dy, d1dy, o, logtab);
+  }
+}
+
 // Edge kernel: the O(xdim + ydim) output nodes on the grid boundary (global rows 0 and
 // ydim-1 in full, columns 0 and xdim-1 of the other rows) with numpy's one-sided formulas.
 template <int KIND, int MODE, bool XI, class Loader>
