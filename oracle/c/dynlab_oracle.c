@@ -182,7 +182,7 @@ typedef struct {
 static void rk45_solve(int id, const double* p, int n, const double* y0, double t0, double tf,
                        double rtol, const double* atol, double max_step, double first_step,
                        double* y_out, orc_stats* st) {
-  double y[ORC_MAXDIM], f[ORC_MAXDIM], K[7][ORC_MAXDIM], ynew[ORC_MAXDIM], tmp[ORC_MAXDIM],
+  double y[ORC_MAXDIM], f[ORC_MAXDIM], K[7][ORC_MAXDIM], ynew[ORC_MAXDIM] = {0}, tmp[ORC_MAXDIM],
       scale[ORC_MAXDIM];
   st->nfev = st->naccept = st->nreject = 0;
   st->status = 0;
