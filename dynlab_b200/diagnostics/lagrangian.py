@@ -73,6 +73,7 @@ class FTLE(LagrangianDiagnostic2D):
     # behind K1.  Results are bit-identical to the one-shot path (seeds are independent and the
     # stencil of a row only reads its neighbour rows).
     pipeline_chunks = 4
+    pipeline_last_fraction = 32  # the last chunk is ydim / 32 rows (chunks 3-8, fractions 16-64: all within 0.5 %)
 
     def _compute_pipelined(self, plan, t, edge_order):
         if edge_order > 2:
@@ -80,7 +81,7 @@ class FTLE(LagrangianDiagnostic2D):
         eng = Engine.get()
         n, ydim, xdim = self.pipeline_chunks, self.ydim, self.xdim
         # equal chunks except a short last one: only its device-to-host copy is left exposed
-        last = max(64, ydim // (4 * n))
+        last = max(64, ydim // self.pipeline_last_fraction)
         bounds = [(ydim - last) * c // (n - 1) for c in range(n)] + [ydim]
         fm = eng.empty(ydim, xdim, 2)
         field = eng.empty(ydim, xdim)
