@@ -45,11 +45,67 @@ __global__ void __launch_bounds__(FE_BLOCK) flow_eval_kernel(const EvalParams P)
   }
 }
 
+// Grid mode for x/y-separable flows (flows.cuh: FlowXY): a CTA owns 128 columns x FE_TROWS
+// rows; every thread evaluates the x part of its column once, the CTA evaluates the y parts of
+// the tile's rows once into shared memory, and a node costs flow_combine plus two coalesced
+// stores - the kernel becomes write-bound (16 B/node) instead of transcendental-bound.  Values
+// are bit-identical to the per-node kernel above (same operations on the same intermediates).
+constexpr int FE_TCOLS = 128;
+constexpr int FE_TROWS = 128;
+
+template <int ID>
+__global__ void __launch_bounds__(FE_TCOLS) flow_eval_tile_kernel(const EvalParams P, long long ydim) {
+  constexpr int NX = FlowXY<ID>::NX > 0 ? FlowXY<ID>::NX : 1;
+  constexpr int NY = FlowXY<ID>::NY > 0 ? FlowXY<ID>::NY : 1;
+  __shared__ double yps[FE_TROWS][NY];
+  const long long xdim = P.xdim;
+  const long long nstrips = (xdim + FE_TCOLS - 1) / FE_TCOLS;
+  const long long nchunks = (ydim + FE_TROWS - 1) / FE_TROWS;
+  const int t = threadIdx.x;
+  dm::TrigSafe trig;
+  double tcs[1][FlowTime<ID>::N > 0 ? FlowTime<ID>::N : 1] = {};
+  flow_time<ID, 1>(P.fc, trig, &P.t, tcs);
+  for (long long task = blockIdx.x; task < nstrips * nchunks; task += gridDim.x) {
+    const long long chunk = task / nstrips, strip = task - chunk * nstrips;
+    const long long j = strip * FE_TCOLS + t, r0 = chunk * FE_TROWS;
+    const int nrows = (int)((r0 + FE_TROWS <= ydim) ? FE_TROWS : ydim - r0);
+    double xp[NX];
+    flow_xpart<ID>(P.fc, trig, tcs[0], P.px[(j < xdim) ? j : xdim - 1], xp);
+    __syncthreads();  // the previous task's readers are done
+    if (t < nrows) {
+      double yp[NY];
+      flow_ypart<ID>(P.fc, trig, tcs[0], P.py[r0 + t], yp);
+#pragma unroll
+      for (int q = 0; q < NY; ++q) yps[t][q] = yp[q];
+    }
+    __syncthreads();
+    if (j < xdim) {
+      long long o = r0 * xdim + j;
+      for (int r = 0; r < nrows; ++r, o += xdim) {
+        double yp[NY], out[2];
+#pragma unroll
+        for (int q = 0; q < NY; ++q) yp[q] = yps[r][q];
+        flow_combine<ID>(xp, yp, out);
+        P.u[o] = out[0];
+        P.v[o] = out[1];
+      }
+    }
+  }
+}
+
 template <int ID, bool GRID>
 int launch_eval(const EvalParams& P, cudaStream_t stream) {
   int dev = 0, sms = 0;
   DLB_CUDA_CHECK(cudaGetDevice(&dev));
   DLB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if constexpr (GRID && FlowXY<ID>::NX > 0) {
+    const long long ydim = P.n / P.xdim;
+    long long tiles = ((P.xdim + FE_TCOLS - 1) / FE_TCOLS) * ((ydim + FE_TROWS - 1) / FE_TROWS);
+    if (tiles > (long long)sms * 16) tiles = (long long)sms * 16;
+    flow_eval_tile_kernel<ID><<<(unsigned)tiles, FE_TCOLS, 0, stream>>>(P, ydim);
+    DLB_CUDA_CHECK(cudaGetLastError());
+    return DLB_OK;
+  }
   long long blocks = (P.n + FE_BLOCK - 1) / FE_BLOCK;
   if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
   if (blocks < 1) blocks = 1;

@@ -512,6 +512,12 @@ def test_fused_flow_stencil_equals_two_kernel_path(dl):
             ydim = len(y)
             eo = 1 + gi % 2
             u, v = eng.flow_eval_grid(fid, params, 0.37, x, y)
+            # grid mode (separable tile kernel where the flow allows) == per-point evaluation
+            X, Y = np.meshgrid(x, y)
+            pts = torch.tensor(np.stack([X.ravel(), Y.ravel()]), device=eng.device)
+            up = eng.flow_eval_points(fid, 2, params, 0.37, pts)
+            assert torch.equal(up[0].view(torch.int64), u.reshape(-1).view(torch.int64)), name
+            assert torch.equal(up[1].view(torch.int64), v.reshape(-1).view(torch.int64)), name
             for mode, xim in modes:
                 neg = mode == nat.EULER_S_MIN and xim == nat.XI_FORCED
                 ref = eng.euler_stencil(mode, u, v, 0, x, y, eo, 0, ydim, neg, xim)
