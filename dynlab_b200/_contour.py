@@ -1,10 +1,10 @@
-"""Zero-contour extraction of a masked grid (host side of RidgeExtractor2D.extract_ridges).
+"""Zero-contour extraction of a masked grid (last step of RidgeExtractor2D.extract_ridges).
 
 The reference calls ``contourpy.contour_generator(x=, y=, z=masked).lines(0)``
 (R:src/dynlab/diagnostics/_base_classes.py:270): default "serial" algorithm, ``corner_mask``
 on (z is a masked array), ``LineType.Separate`` -> ``list[np.ndarray[n, 2]]`` of (x, y) vertices.
-When contourpy is importable it is used directly (it is the reference's own dependency);
-otherwise ``marching_squares`` below produces the polylines with contourpy's conventions:
+The product path is ``zero_contour_lines_device``: cell classification on the device
+(csrc/contour.cu), polyline linking in C++ (csrc/link.cu), with contourpy's conventions:
 
 * a node is "upper" iff ``z > level``;
 * a quad contributes if none of its corners is masked; a quad with exactly one masked corner
@@ -22,21 +22,14 @@ R:tests/test_diagnostics/test_eulerian.py:127-181) from the reference's ridge fi
 tests/test_contour.py.  contourpy itself is not installed in the build image, so configurations
 those goldens do not exercise (several starts in one cell, closed-loop start vertex) follow
 this module's own deterministic choice.
+
+``marching_squares`` / ``link_segments`` are the all-numpy twins of the two native stages; they
+exist as the cross-check the tests compare the native path against and are not called by the
+diagnostics.
 """
 from __future__ import annotations
 
 import numpy as np
-
-try:  # pragma: no cover - not available in the build image
-    from contourpy import contour_generator as _contourpy_generator
-except Exception:  # noqa: BLE001
-    _contourpy_generator = None
-
-
-def zero_contour_lines(x, y, z, level: float = 0.0):
-    if _contourpy_generator is not None:  # pragma: no cover
-        return _contourpy_generator(x=x, y=y, z=z).lines(level)
-    return marching_squares(np.asarray(x, dtype=float), np.asarray(y, dtype=float), z, level)
 
 
 def _cell_segments(zd, mask, above, level):

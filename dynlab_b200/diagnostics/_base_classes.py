@@ -307,8 +307,8 @@ class RidgeExtractor2D(Diagnostic2D, ABC):
 
     def extract_ridges(self, field, Xi, percentile, edge_order, debug=False):
         """``field`` / ``Xi``: device tensors ``[ydim, xdim]`` / ``[ydim, xdim, 2]``.
-        The gradient/Hessian/mask stage runs on the device; the zero-contour of the masked
-        directional-derivative field is traced on the host (O(ridge length) output)."""
+        Gradient / Hessian / masks, the percentile threshold and the contour cell pass run on
+        the device; only the O(ridge length) segment records come back to be linked."""
         from .. import _contour
 
         eng = Engine.get()
@@ -318,15 +318,10 @@ class RidgeExtractor2D(Diagnostic2D, ABC):
             # on the device (csrc/select.cu) and interpolated like numpy
             threshold = eng.percentile(field, percentile)
         dd, conc, mask = eng.ridge_field(field, Xi, self._xf, self._yf, edge_order, threshold)
-        dd_h = None
-        if _contour._contourpy_generator is not None:  # pragma: no cover - the reference's own
-            dd_h = np.ma.MaskedArray(eng.to_host(dd), mask=eng.to_host(mask).astype(bool))
-            ridge_lines = _contour.zero_contour_lines(self.x, self.y, dd_h)
-        else:  # cell classification on the device, polyline linking on the host
-            ridge_lines = _contour.zero_contour_lines_device(eng, dd, mask, self._xf, self._yf)
+        # cell classification on the device, polyline linking in C++ (host, O(ridge length))
+        ridge_lines = _contour.zero_contour_lines_device(eng, dd, mask, self._xf, self._yf)
         if debug:
-            if dd_h is None:
-                dd_h = np.ma.MaskedArray(eng.to_host(dd), mask=eng.to_host(mask).astype(bool))
-            self.directional_derivative = dd_h
+            self.directional_derivative = np.ma.MaskedArray(
+                eng.to_host(dd), mask=eng.to_host(mask).astype(bool))
             self.concavity = np.ma.MaskedArray(eng.to_host(conc))
         return ridge_lines

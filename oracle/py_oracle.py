@@ -19,7 +19,6 @@ Ridge *contour* geometry (contourpy) is "parity unpinned": contourpy is absent.
 """
 from __future__ import annotations
 
-import math
 import os
 from itertools import product
 
