@@ -142,9 +142,12 @@ class Engine:
     # and the pinned blocks stay allocated.  Loops over many fields may prefer True.
     PINNED_RESULTS = False
 
-    def to_host(self, t: torch.Tensor) -> np.ndarray:
-        """Device tensor -> numpy array (see ``PINNED_RESULTS`` for large ones)."""
-        if (not self.PINNED_RESULTS and t.dtype == _F64
+    def to_host(self, t: torch.Tensor, pinned=None) -> np.ndarray:
+        """Device tensor -> numpy array (see ``PINNED_RESULTS`` for large ones; ``pinned``
+        overrides it for one call)."""
+        if pinned is None:
+            pinned = self.PINNED_RESULTS
+        if (not pinned and t.dtype == _F64
                 and t.numel() * t.element_size() >= 4 * self.H2D_CHUNK):
             return self._to_host_staged(t)
         h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)

@@ -60,7 +60,10 @@ class FTLE(LagrangianDiagnostic2D):
             return self._compute_shared(x, y, f, t, edge_order, kwargs)
         field = self._run(x, y, f, t, edge_order, self.gather_flow_map, kwargs)
         if sharding.host_result_wanted():
-            self.field = np.ma.MaskedArray(Engine.get().to_host(field))
+            # several ranks copying at once: the staged path's worker threads and page faults
+            # contend for the host cores, one DMA into a pinned buffer per rank does not
+            many = sharding.world()[1] > 1
+            self.field = np.ma.MaskedArray(Engine.get().to_host(field, pinned=True if many else None))
         else:  # sharding.set_host_result("rank0") on a non-zero rank: placeholder, all masked
             torch.cuda.current_stream(field.device).synchronize()
             self.field = np.ma.MaskedArray(np.broadcast_to(np.nan, tuple(field.shape)), mask=True)
