@@ -214,6 +214,9 @@ def run_ours(args):
     from dynlab_b200.diagnostics import FTLE
     from dynlab_b200.flows import double_gyre
 
+    if args.halo:
+        sharding.set_halo_mode(args.halo)
+
     eng = Engine.get()
     x, y = grid(1)
     n_seeds = XDIM * YDIM
@@ -315,8 +318,8 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "FTLE double_gyre 8192x4096, t=(10,0), edge_order=2, "
                                    "rtol=atol=1e-8 (BASELINE configs[2])",
-                       "parallelism": f"row slabs over {world} GPU(s); 1-row halo exchange + "
-                                      "all-gather" if world > 1 else "single GPU",
+                       "parallelism": f"row slabs over {world} GPU(s); halo rows: "
+                                      f"{sharding.halo_mode()}; all-gather" if world > 1 else "single GPU",
                        "l2": "inputs/outputs (537 MB flow map + 268 MB field per step) exceed "
                              "the 126 MB L2; no flush needed",
                        "integrator": {"mean_nfev_per_seed": stats["nfev"] / max(stats["seeds"], 1),
@@ -372,6 +375,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--halo", choices=["exchange", "redundant"], default=None,
+                    help="multi-GPU: how ranks obtain the halo rows (default: the library's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -28,6 +28,24 @@ def set_distributed(mode) -> None:
     _mode = "auto" if mode in (True, "auto") else "off"
 
 
+_halo = "exchange"
+
+
+def set_halo_mode(mode) -> None:
+    """How a rank obtains the flow-map rows just outside its slab that the stencil needs:
+    ``"exchange"``: one row from each neighbour (``exchange_halo``); ``"redundant"``: integrate
+    those rows locally too (SURVEY §8e's alternative: 2 extra rows per slab, no data-path
+    communication before the final gather, bit-identical because seeds are independent)."""
+    global _halo
+    if mode not in ("exchange", "redundant"):
+        raise ValueError('mode must be "exchange" or "redundant"')
+    _halo = mode
+
+
+def halo_mode() -> str:
+    return _halo
+
+
 _host_result = "all"  # which ranks receive the gathered field in host memory
 
 

@@ -23,6 +23,9 @@ for (nx, ny, eo) in ((257, 131, 2), (64, 5, 1), (33, 3, 2), (1024, 512, 2)):
     d = FTLE()
     f_sh = np.ma.getdata(d.compute(x, y, double_gyre, (6, 0), edge_order=eo, rtol=1e-8, atol=1e-8)).copy()
     fm_sh = d.flow_map.copy()
+    sharding.set_halo_mode("redundant")  # halo rows integrated locally instead of exchanged
+    f_red = np.ma.getdata(FTLE().compute(x, y, double_gyre, (6, 0), edge_order=eo, rtol=1e-8, atol=1e-8)).copy()
+    sharding.set_halo_mode("exchange")
     sharding.set_host_result("shared")  # one pinned host segment, each rank copies its own rows
     f_shm = np.ma.getdata(FTLE().compute(x, y, double_gyre, (6, 0), edge_order=eo, rtol=1e-8, atol=1e-8)).copy()
     sharding.set_host_result("all")
@@ -39,7 +42,7 @@ for (nx, ny, eo) in ((257, 131, 2), (64, 5, 1), (33, 3, 2), (1024, 512, 2)):
     l.compute(x, y, f=double_gyre, t=(6, 0), edge_order=eo, percentile=70, debug=True, rtol=1e-8, atol=1e-8)
     a_1 = np.ma.getdata(AttractionRate().compute(x * 1e4, y * 8e3 - 4e3, f=bickley_jet, t=0.1, edge_order=eo))
     r = TrajectoryRepulsionRate().compute(x, y, f=double_gyre, t=0.3, edge_order=eo)
-    same = (np.array_equal(f_sh, f_1) and np.array_equal(f_shm, f_1) and np.array_equal(fm_sh, d.flow_map)
+    same = (np.array_equal(f_sh, f_1) and np.array_equal(f_shm, f_1) and np.array_equal(f_red, f_1) and np.array_equal(fm_sh, d.flow_map)
             and np.array_equal(xi_sh, np.ma.getdata(l.Xi_max)) and np.array_equal(a_sh, a_1)
             and np.array_equal(r_sh, np.ma.getdata(r)) and np.array_equal(rm_sh, np.ma.getmaskarray(r)))
     ok = ok and same
