@@ -285,3 +285,34 @@ def test_shared_host_segment_gloo(tmp_path, size):
     port = 31500 + (os.getpid() + size * 13) % 2000
     mp.spawn(_shared_worker, args=(size, port, str(tmp_path)), nprocs=size, join=True)
     assert os.path.exists(tmp_path / "ok_shared")
+
+
+def test_sharding_mode_switches_validate():
+    from dynlab_b200 import sharding
+
+    assert sharding.halo_mode() == "exchange"
+    sharding.set_halo_mode("redundant")
+    assert sharding.halo_mode() == "redundant"
+    sharding.set_halo_mode("exchange")
+    with pytest.raises(ValueError):
+        sharding.set_halo_mode("both")
+    with pytest.raises(ValueError):
+        sharding.set_host_result("nobody")
+    assert sharding.host_result_wanted() and not sharding.host_result_shared()  # no process group
+
+
+def test_deferred_attribute_resolves_once():
+    """_LazyHost + _Deferred (u, v of the fused Eulerian path): the producer runs once, only when
+    an attribute is read, and both attributes share its result."""
+    from dynlab_b200.diagnostics._base_classes import _Deferred
+
+    calls = []
+
+    def produce():
+        calls.append(1)
+        return ("U", "V")
+
+    cache = {}
+    du, dv = _Deferred(produce, 0, cache), _Deferred(produce, 1, cache)
+    assert not calls
+    assert dv.resolve() == "V" and du.resolve() == "U" and len(calls) == 1
