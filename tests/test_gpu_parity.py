@@ -378,6 +378,56 @@ def test_lcs_fields_against_reference(dl, golden, name, x, y, t, eo, pct):
         assert np.abs(np.ma.getdata(l.directional_derivative) - dd_ref)[both].max() < 1e-6 * sc
 
 
+def test_readme_examples_through_dynlab_alias(dl, golden):
+    """The five usage examples of the reference's README (R:README.md:20-26, :31-38, :44-51,
+    :64-71, :78-84), unmodified apart from the plotting lines, after
+    ``dynlab_b200.install_as_dynlab()`` - i.e. what a user who switches packages runs."""
+    import importlib
+
+    from oracle import py_oracle as po
+
+    dl.install_as_dynlab()
+    FTLE = importlib.import_module("dynlab.diagnostics").FTLE
+    from dynlab.diagnostics import LCS, AttractionRate, TrajectoryRepulsionRate, iLES
+    from dynlab.flows import bead_on_a_rotating_hoop, bickley_jet, double_gyre
+
+    # FTLE (README :20-26) against the reference's own output for exactly this call
+    x = np.linspace(0, 2, 101)
+    y = np.linspace(0, 1, 101)
+    ftle = FTLE(num_threads=1).compute(x, y, double_gyre, (10, 0), edge_order=2, rtol=1e-8, atol=1e-8)
+    ref = golden("ftle_c1")["field"]
+    assert isinstance(ftle, np.ma.MaskedArray) and ftle.shape == (101, 101)
+    assert rel_err(np.ma.getdata(ftle), ref, 1e-3).max() < 1e-6
+    # LCS (README :31-38)
+    x = np.linspace(0, 2, 201)
+    lcs = LCS()
+    attracting_lcs = lcs.compute(x, y, f=double_gyre, t=(10, 0), percentile=80)
+    assert len(attracting_lcs) > 0 and all(l.ndim == 2 and l.shape[1] == 2 for l in attracting_lcs)
+    assert lcs.ftle.shape == (101, 201) and not hasattr(lcs, "flow_map")
+    # iLES (README :44-51)
+    a = iLES().compute(x, y, f=double_gyre, t=0, kind='attracting', force_eigenvectors=True)
+    r = iLES().compute(x, y, f=double_gyre, t=0, kind='repelling', force_eigenvectors=True)
+    assert len(a) > 0 and len(r) > 0
+    # AttractionRate on the Bickley jet (README :64-71)
+    x = np.linspace(0, 20000, 101)
+    y = np.linspace(-4000, 4000, 101)
+    u, v = bickley_jet(0, np.meshgrid(x, y))
+    attraction_rate = AttractionRate().compute(x, y, u=u, v=v, edge_order=2)
+    exp = po.attraction_repulsion_rate(x, y, u=u, v=v, edge_order=2)
+    sc = np.abs(np.ma.getdata(exp)).max()
+    assert np.abs(np.ma.getdata(attraction_rate) - np.ma.getdata(exp)).max() < 1e-9 * sc
+    assert (-attraction_rate).shape == (101, 101)  # the README plots the negated field
+    # TrajectoryRepulsionRate of the bead (README :78-84; a coarser grid for the Python oracle)
+    x = np.linspace(-1, 1, 61) * 3
+    y = np.linspace(-1, 1, 41) * 2.5
+    rhodot = TrajectoryRepulsionRate().compute(x, y, f=bead_on_a_rotating_hoop, t=0, edge_order=2)
+    exp = po.trajectory_repulsion(x, y, f=po.flow("bead_on_a_rotating_hoop"), t=0, edge_order=2)
+    assert np.array_equal(np.ma.getmaskarray(rhodot), np.ma.getmaskarray(exp))
+    ok = ~np.ma.getmaskarray(exp)
+    sc = np.abs(np.ma.getdata(exp)[ok]).max()
+    assert np.abs(np.ma.getdata(rhodot) - np.ma.getdata(exp))[ok].max() < 1e-9 * sc
+
+
 def test_reference_ridge_tests_through_api(dl):
     """R:tests/test_diagnostics/test_lagrangian.py:20-44 (test_lcs) and
     R:tests/test_diagnostics/test_eulerian.py:126-193 (test_iles, test_iles_with_forced_
