@@ -316,3 +316,18 @@ def test_deferred_attribute_resolves_once():
     du, dv = _Deferred(produce, 0, cache), _Deferred(produce, 1, cache)
     assert not calls
     assert dv.resolve() == "V" and du.resolve() == "U" and len(calls) == 1
+
+
+def test_ctypes_signatures_match_header_arity():
+    """Every prototype of include/dynlab_b200.h has as many parameters as the ctypes binding
+    declares (a missing argument would shift everything after it silently)."""
+    from dynlab_b200 import _native
+
+    header = open(os.path.join(ROOT, "include", "dynlab_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = re.findall(r"\b(dlb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) == len(_native.SIGNATURES)
+    for name, params in protos:
+        params = " ".join(params.split())
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_native.SIGNATURES[name][1]), (name, n, len(_native.SIGNATURES[name][1]))
