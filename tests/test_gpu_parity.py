@@ -831,6 +831,47 @@ def test_ftle_c3_full_size_properties(dl):
     assert (back - seeds).abs().max().item() < 1e-5
 
 
+def test_four_times_config3_no_index_overflow(dl):
+    """16384 x 8192 = 134 M seeds (4 x BASELINE config 3, 2.1 GB flow map: element offsets pass
+    2^28, byte offsets 2^31): K1 + K2 on the device, strided seeds and corner / interior patches
+    against the C oracle, the field against numpy on the same flow map, the LCS-side kernels
+    (percentile, contour) on the full field."""
+    from dynlab_b200._engine import Engine
+    from oracle import c_oracle as co
+    from oracle import py_oracle as po
+
+    nx, ny = 16384, 8192
+    x, y = np.linspace(0, 2, nx), np.linspace(0, 1, ny)
+    d = dl.diagnostics.FTLE()
+    f_dev = d.compute_device(x, y, dl.flows.double_gyre, (2, 0), edge_order=2, rtol=1e-8, atol=1e-8)
+    eng = Engine.get()
+    st = eng.read_counters()
+    assert st["seeds"] == nx * ny and st["failed"] == 0
+    fm_dev = d.__dict__["_flow_map_dev"]
+    p = po.flow_params("double_gyre")
+    ref, _, _ = co.flow_map("double_gyre", p, x[::128], y[::128], 2.0, 0.0, 1e-8, 1e-8)
+    assert np.abs(fm_dev[::128, ::128].cpu().numpy() - ref).max() < 1e-11
+    for (i0, j0) in ((ny - 40, nx - 40), (0, nx - 40), (ny - 40, 0), (5000, 9000)):
+        fm = fm_dev[i0:i0 + 40, j0:j0 + 40].cpu().numpy()
+        pf, _, _ = co.flow_map("double_gyre", p, x[j0:j0 + 40], y[i0:i0 + 40], 2.0, 0.0, 1e-8, 1e-8)
+        assert np.abs(fm - pf).max() < 1e-11
+    for sl in (slice(0, 32), slice(ny - 32, ny), slice(6000, 6032)):
+        lo, hi = max(sl.start - 2, 0), min(sl.stop + 2, ny)
+        ref_rows = np.ma.getdata(po.ftle_from_flow_map(fm_dev[lo:hi].cpu().numpy(), x, y[lo:hi], (2, 0), 2))
+        a = f_dev[sl].cpu().numpy()
+        b = ref_rows[sl.start - lo: sl.start - lo + 32]
+        inner = slice(0, 30) if sl.start == 0 else slice(2, 32) if sl.stop == ny else slice(0, 32)
+        assert rel_err(a[inner], b[inner], 1e-3).max() < 1e-7
+    # order statistics and contour cells over 134 M nodes
+    q = eng.percentile(f_dev, 90)
+    sample = f_dev[::16, ::16].cpu().numpy()
+    assert abs(q - np.percentile(sample, 90)) < 0.05 * max(abs(q), 1e-3)
+    cell, ka, kb, pts = eng.contour_segments(f_dev, None, x, y, level=q)
+    assert len(cell) > 1000 and cell.min() >= 0 and cell.max() < (nx - 1) * (ny - 1)
+    assert pts[:, 0].min() >= 0 and pts[:, 0].max() <= 2 and pts[:, 1].min() >= 0 and pts[:, 1].max() <= 1
+    assert (ka < nx * ny * nx * ny).all() and (ka >= 0).all() and (kb >= 0).all()
+
+
 def test_config4_full_size_samples(dl):
     """BASELINE config 4 at full size (4096x4096): FTLE of bead_on_a_rotating_hoop t=(0,2) and
     of duffing_oscillator t=(10,0) (step counts 476..2456 per seed) against the C oracle on a
