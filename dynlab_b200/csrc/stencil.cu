@@ -9,16 +9,20 @@
 // (f[i+1]-f[i-1])/(2h) (:1305), non-uniform interior a f[i-1] + b f[i] + c f[i+1] (:1307-1318),
 // edge_order 1 two-point (:1321-1334), edge_order 2 three-point (:1337-1372).
 //
-// B200 mapping (HBM-bound, 24 B per point).  Interior kernel: one warp walks 32 consecutive
-// columns down a chunk of rows keeping the rows i-1, i, i+1 of its column in registers (next
-// row prefetched), so every element is requested once as a coalesced 256/512 B row segment;
-// the x neighbours come from the adjacent lanes by warp shuffle (30 output columns per warp).
-// The O(xdim + ydim) boundary nodes — numpy's one-sided formulas — run in a separate small
-// edge kernel, which keeps the interior loop free of edge logic (64 registers, no spills).
-// Coefficients are precomputed per row / per column on the host with numpy's own formulas
-// (true divisions), so the kernels have no FP64 divides on the interior path; sqrt and log
-// are branch-free MUFU-seeded Newton / series versions.  Grids are multiples of the SM count
-// and warps grid-stride over (strip, row-chunk) tasks.
+// B200 mapping (24 B per point in, 8 out).  Three interior kernels, newest first:
+//   * stencil_tma_kernel (default): TMA tile copies (cp.async.bulk.tensor.2d) into a staged
+//     shared-memory ring, 128 threads = 128 tile columns, rows of a stage fully unrolled,
+//     branch-free epilogue with predicated stores;
+//   * stencil_bulk_kernel: 1-D bulk copies per row into an 8-row ring (fallback when no tensor
+//     map can be encoded; DLB_STENCIL_TMA=0);
+//   * stencil_interior_kernel: one warp walks 32 columns with a renamed register window and warp
+//     shuffles (unaligned rows: SoA fields with odd xdim; DLB_STENCIL_BULK=0).
+// The O(xdim + ydim) boundary nodes — numpy's one-sided formulas — run in a separate small edge
+// kernel, which keeps the interior loops free of edge logic.  Coefficients are precomputed per
+// row / per column on the host with numpy's own formulas (true divisions) and cached in the
+// workspace, so the kernels have no FP64 divides on the interior path; sqrt and log are
+// branch-free MUFU-seeded Newton / table versions.  Device helpers shared with eulerflow.cu live
+// in stencil_device.cuh.
 #include <math.h>
 #include <math_constants.h>
 
