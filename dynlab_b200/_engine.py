@@ -271,13 +271,15 @@ class Engine:
 
     # -- K2 ---------------------------------------------------------------------------
     def ftle_stencil(self, fm_local, grow0, x, y, edge_order, t_span, out_row0, out_rows,
-                     xi_mode=nat.XI_NONE, out=None):
+                     xi_mode=nat.XI_NONE, out=None, xi_out=None):
         xdim, ydim = len(x), len(y)
         nloc = fm_local.shape[0]
         with torch.cuda.device(self.device):
             if out is None:
                 out = self.empty(out_rows, xdim)
-            xi = self.empty(out_rows, xdim, 2) if xi_mode != nat.XI_NONE else None
+            xi = None
+            if xi_mode != nat.XI_NONE:
+                xi = xi_out if xi_out is not None else self.empty(out_rows, xdim, 2)
             ws, wsz = self.workspace(xdim, ydim)
             with self._timed("ftle_stencil", 2):
               nat.check(nat.lib.dlb_ftle_stencil(
@@ -352,12 +354,18 @@ class Engine:
         return out
 
     # -- ridge field ------------------------------------------------------------------
-    def ridge_field(self, field, xi, x, y, edge_order, threshold=None):
+    def ridge_buffers(self, xdim, ydim):
+        """(dd, conc, mask, scratch) for ``ridge_field`` - callers that sit behind a host sync
+        allocate them earlier, while the device is still busy (cudaMalloc of result-sized blocks
+        that cannot come from the cache costs milliseconds)."""
+        with torch.cuda.device(self.device):
+            return (self.empty(ydim, xdim), self.empty(ydim, xdim),
+                    self.empty(ydim, xdim, dtype=torch.uint8), self.empty(ydim, xdim, 2))
+
+    def ridge_field(self, field, xi, x, y, edge_order, threshold=None, bufs=None):
         xdim, ydim = len(x), len(y)
         with torch.cuda.device(self.device):
-            dd, conc = self.empty(ydim, xdim), self.empty(ydim, xdim)
-            mask = self.empty(ydim, xdim, dtype=torch.uint8)
-            scratch = self.empty(ydim, xdim, 2)
+            dd, conc, mask, scratch = bufs if bufs is not None else self.ridge_buffers(xdim, ydim)
             ws, wsz = self.workspace(xdim, ydim)
             with self._timed("ridge_field", 2):
               nat.check(nat.lib.dlb_ridge_field(
@@ -370,17 +378,23 @@ class Engine:
     # -- contour segments -------------------------------------------------------------
     _contour_cap = 0  # largest segment count seen so far (+ head room): avoids re-launches
 
-    def contour_launch(self, z, mask, x, y, level=0.0, cap=None):
+    def contour_buffers(self, xdim, ydim, cap=None):
+        """(cap, count, cell, key_a, key_b, pts) record buffers for ``contour_launch``."""
+        with torch.cuda.device(self.device):
+            cap = int(cap or max(1 << 16, 8 * (xdim + ydim), self._contour_cap))
+            return (cap, torch.zeros(1, dtype=torch.int64, device=self.device),
+                    self.empty(cap, dtype=torch.int64), self.empty(cap, dtype=torch.int64),
+                    self.empty(cap, dtype=torch.int64), self.empty(cap, 4))
+
+    def contour_launch(self, z, mask, x, y, level=0.0, cap=None, bufs=None):
         """Enqueue the device pass of the contour extraction on the current stream; returns a
         handle for ``contour_fetch``.  Nothing is synchronised."""
         xdim, ydim = len(x), len(y)
         with torch.cuda.device(self.device):
             ws, wsz = self.workspace(xdim, ydim)
-            cap = int(cap or max(1 << 16, 8 * (xdim + ydim), self._contour_cap))
-            count = torch.zeros(1, dtype=torch.int64, device=self.device)
-            cell = self.empty(cap, dtype=torch.int64)
-            ka, kb = self.empty(cap, dtype=torch.int64), self.empty(cap, dtype=torch.int64)
-            pts = self.empty(cap, 4)
+            if bufs is None:
+                bufs = self.contour_buffers(xdim, ydim, cap)
+            cap, count, cell, ka, kb, pts = bufs
             with self._timed("contour_segments"):
                 nat.check(nat.lib.dlb_contour_segments(
                     z.data_ptr(), mask.data_ptr() if mask is not None else None, nat.dptr(x),

@@ -10,6 +10,7 @@ unless ``to_host`` is set.
 from __future__ import annotations
 
 import numpy as np
+import torch
 import torch.distributed as dist
 
 from . import _native as nat
@@ -18,6 +19,11 @@ from ._contour import contour_lines_finish
 from ._engine import Engine, as_coord
 from ._resolve import resolve_flow
 from .utils import ODEINT_DEFAULT_TOL, parse_integrator_kwargs
+
+
+def handle_cap_grew(eng, cbufs) -> bool:
+    """True when a previous slice needed more contour records than the reusable buffers hold."""
+    return eng._contour_cap > cbufs[0]
 
 
 def ftle_time_sweep(x, y, f, t_spans, edge_order: int = 1, percentile=None, ridge: bool = False,
@@ -47,6 +53,19 @@ def ftle_time_sweep(x, y, f, t_spans, edge_order: int = 1, percentile=None, ridg
     out = {}
     fm = eng.empty(ydim, xdim, 2)
     pending = None  # (slice, contour handle, device results): linked while the next slice integrates
+    # All device memory of the sweep is taken here, once: the results of every owned slice as
+    # stacked tensors (they are handed out as views), the temporaries as one reusable set.  With
+    # per-slice allocations torch's caching allocator had to cudaMalloc / cudaFree result-sized
+    # blocks in the middle of the sweep (freed xi / scratch blocks get split by the retained
+    # results), and cudaFree waits for the running K1: stalls of 80-250 ms on some slices.
+    owned = [k for k in range(len(t_spans)) if k % size == rank]
+    n_keep = len(owned) if not to_host else 1
+    fields = eng.empty(max(n_keep, 1), ydim, xdim)
+    if ridge:
+        dds = eng.empty(max(n_keep, 1), ydim, xdim)
+        masks = eng.empty(max(n_keep, 1), ydim, xdim, dtype=torch.uint8)
+        xi_buf, conc_buf, scratch = eng.empty(ydim, xdim, 2), eng.empty(ydim, xdim), eng.empty(ydim, xdim, 2)
+        cbufs = eng.contour_buffers(xdim, ydim)
 
     def finish(p):
         k, handle, field, dd, mask = p
@@ -65,7 +84,9 @@ def ftle_time_sweep(x, y, f, t_spans, edge_order: int = 1, percentile=None, ridg
             finish(pending)
             pending = None
         xi_mode = nat.XI_LAPACK if ridge else nat.XI_NONE
-        field, xi = eng.ftle_stencil(fm, 0, xs, ys, edge_order, abs(tf - t0), 0, ydim, xi_mode)
+        slot = owned.index(k) if not to_host else 0
+        field, xi = eng.ftle_stencil(fm, 0, xs, ys, edge_order, abs(tf - t0), 0, ydim, xi_mode,
+                                     out=fields[slot], xi_out=xi_buf if ridge else None)
         if not ridge:
             out[k] = np.ma.MaskedArray(eng.to_host(field)) if to_host else field
             continue
@@ -73,8 +94,11 @@ def ftle_time_sweep(x, y, f, t_spans, edge_order: int = 1, percentile=None, ridg
         if percentile:
             # R:_base_classes.py:266-268 — np.percentile of the (unmasked) field values
             thr = eng.percentile(field, percentile)
-        dd, conc, mask = eng.ridge_field(field, xi, xs, ys, edge_order, thr)
-        handle = eng.contour_launch(dd, mask, xs, ys)
+        dd, _, mask = eng.ridge_field(field, xi, xs, ys, edge_order, thr,
+                                      bufs=(dds[slot], conc_buf, masks[slot], scratch))
+        if handle_cap_grew(eng, cbufs):
+            cbufs = eng.contour_buffers(xdim, ydim)
+        handle = eng.contour_launch(dd, mask, xs, ys, bufs=cbufs)
         if to_host:
             field = np.ma.MaskedArray(eng.to_host(field))
             dd = np.ma.MaskedArray(eng.to_host(dd), mask=eng.to_host(mask).astype(bool))
