@@ -137,6 +137,10 @@ extern "C" int dlb_order_statistics(const double* d_values, int64_t n, const int
     dlb_set_error("dlb_order_statistics: bad argument (n >= 1, 1 <= nranks <= 2)");
     return DLB_ERR_ARG;
   }
+  if (n >= ((int64_t)1 << 32)) {  // the per-digit histograms are 32-bit counters
+    dlb_set_error("dlb_order_statistics: more than 2^32 - 1 values");
+    return DLB_ERR_ARG;
+  }
   if (scratch_bytes < sizeof(SelState)) {
     dlb_set_error("dlb_order_statistics: scratch too small (dlb_select_scratch_bytes)");
     return DLB_ERR_WORKSPACE;
