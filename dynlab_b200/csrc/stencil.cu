@@ -586,13 +586,14 @@ int launch_tma(const StencilParams& P, const CUtensorMap& m0, const CUtensorMap&
                long long ntasks, cudaStream_t stream) {
   auto kern = stencil_tma_kernel<KIND, MODE, XI, AOS>;
   constexpr int dyn = TM_STAGES * TM_STAGE_BYTES;
-  static bool configured = false;
-  static int per_sm = 1;
-  if (!configured) {
+  static int per_sm_of[64] = {0};  // per device: the attribute is a per-device setting
+  int dev = 0;
+  DLB_CUDA_CHECK(cudaGetDevice(&dev));
+  int& per_sm = per_sm_of[dev & 63];
+  if (per_sm == 0) {
     DLB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     DLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TM_THREADS, dyn));
     if (per_sm < 1) per_sm = 1;
-    configured = true;
   }
   long long blocks = (long long)num_sms() * per_sm;
   if (blocks > ntasks) blocks = ntasks;
