@@ -70,77 +70,92 @@ class FTLE(LagrangianDiagnostic2D):
         self._collect_stats()
         return self.field
 
-    # Large single-GPU grids: K1 runs in row chunks; as soon as a chunk's successor row exists
-    # K2 produces that chunk's FTLE rows and a copy stream moves them to pinned host memory
-    # while the next chunk integrates, so the 268 MB device-to-host copy of config 3 hides
-    # behind K1.  Results are bit-identical to the one-shot path (seeds are independent and the
-    # stencil of a row only reads its neighbour rows).
+    # Large grids: K1 runs in row chunks; as soon as a chunk's successor row exists K2 produces
+    # that chunk's FTLE rows and a copy stream moves them to pinned host memory while the next
+    # chunk integrates, so the device-to-host copy (268 MB at config 3) hides behind K1.  Results
+    # are bit-identical to the one-shot path (seeds are independent and the stencil of a row
+    # only reads its neighbour rows).
     pipeline_chunks = 4
-    pipeline_last_fraction = 32  # the last chunk is ydim / 32 rows (chunks 3-8, fractions 16-64: all within 0.5 %)
+    pipeline_last_fraction = 32  # the last chunk is 1/32 of the rows (chunks 3-8, fractions 16-64: all within 0.5 %)
 
-    def _compute_pipelined(self, plan, t, edge_order):
+    def _pipeline(self, plan, t, edge_order, lo, hi, own0, own1, host):
+        """Integrate global rows [lo, hi) in chunks and stream the FTLE rows [own0, own1) into
+        ``host[own0:own1]`` (a pinned torch tensor over the whole grid) as they become
+        computable.  [lo, hi) must contain every row the stencils of [own0, own1) read."""
         if edge_order > 2:
             raise ValueError("'edge_order' greater than 2 not supported")
-        eng = Engine.get()
-        n, ydim, xdim = self.pipeline_chunks, self.ydim, self.xdim
-        # equal chunks except a short last one: only its device-to-host copy is left exposed
-        last = max(64, ydim // self.pipeline_last_fraction)
-        bounds = [(ydim - last) * c // (n - 1) for c in range(n)] + [ydim]
-        fm = eng.empty(ydim, xdim, 2)
-        field = eng.empty(ydim, xdim)
-        host = torch.empty((ydim, xdim), dtype=torch.float64, pin_memory=True)
-        counters = torch.zeros(n, nat.CNT_WORDS, dtype=torch.int64, device=eng.device)
         t_span = abs(float(t[-1]) - float(t[0]))
         if t_span == 0.0:
             raise ZeroDivisionError("float division by zero")  # R:lagrangian.py:71
+        eng = Engine.get()
+        n, nloc, xdim = self.pipeline_chunks, hi - lo, self.xdim
+        if n > 1 and nloc >= 64 * n:
+            # equal chunks except a short last one: only its device-to-host copy is left exposed
+            last = max(64, nloc // self.pipeline_last_fraction)
+            bounds = [lo + (nloc - last) * c // (n - 1) for c in range(n)] + [hi]
+        else:  # small slab: one chunk
+            n, bounds = 1, [lo, hi]
+        fm = eng.empty(nloc, xdim, 2)
+        field = eng.empty(max(own1 - own0, 1), xdim)
+        counters = torch.zeros(n, nat.CNT_WORDS, dtype=torch.int64, device=eng.device)
         main = torch.cuda.current_stream(eng.device)
-        done = 0  # FTLE rows already produced
+        done = own0  # FTLE rows [own0, done) are already produced
         for c in range(n):
             r0, r1 = bounds[c], bounds[c + 1]
-            self._integrate_rows(plan, r0, r1 - r0, fm[r0:r1], counters=counters[c])
-            upto = ydim if r1 == ydim else r1 - 1  # row r1-1 still needs row r1
+            if r1 > r0:
+                self._integrate_rows(plan, r0, r1 - r0, fm[r0 - lo:r1 - lo], counters=counters[c])
+            upto = own1 if r1 == hi else min(own1, r1 - 1)  # row r1-1 still needs row r1
+            if done == 0 and edge_order == 2 and r1 < min(3, hi):
+                upto = done  # the one-sided formula of row 0 reads rows 0..2
             if upto > done:
-                eng.ftle_stencil(fm[:r1], 0, self._xf, self._yf, edge_order, t_span, done,
-                                 upto - done, out=field[done:upto])
+                eng.ftle_stencil(fm[:r1 - lo], lo, self._xf, self._yf, edge_order, t_span, done,
+                                 upto - done, out=field[done - own0:upto - own0])
                 ev = torch.cuda.Event()
                 ev.record(main)
                 eng.copy_stream.wait_event(ev)
                 with torch.cuda.stream(eng.copy_stream):
-                    host[done:upto].copy_(field[done:upto], non_blocking=True)
+                    host[done:upto].copy_(field[done - own0:upto - own0], non_blocking=True)
                 done = upto
         eng.copy_stream.synchronize()
         field.record_stream(eng.copy_stream)
+        self._counters_pending, self._counter_tensors = True, counters
+        return fm, field
+
+    def _compute_pipelined(self, plan, t, edge_order):
+        """Single GPU: the whole grid, result in a fresh pinned buffer."""
+        ydim, xdim = self.ydim, self.xdim
+        host = torch.empty((ydim, xdim), dtype=torch.float64, pin_memory=True)
+        fm, field = self._pipeline(plan, t, edge_order, 0, ydim, 0, ydim, host)
         self.flow_map = fm
         self.field_device = field
         self.field = np.ma.MaskedArray(host.numpy())
-        self._counters_pending, self._counter_tensors = True, counters
         self._collect_stats()
         return self.field
 
     def _compute_shared(self, x, y, f, t, edge_order, kwargs):
-        """Multi-GPU with ``sharding.set_host_result("shared")``: K1 and K2 on this rank's
-        slab, then one device-to-host copy of the slab's FTLE rows into the host segment all
-        ranks of the box map.  No device all-gather; the field crosses PCIe once in total.
-        ``flow_map`` / ``field_device`` hold this rank's rows only."""
-        keep, self.gather_flow_map = self.gather_flow_map, False
-        try:
-            local, slab = LagrangianDiagnostic2D.compute(self, x, y, f, t, **kwargs)
-        finally:
-            self.gather_flow_map = keep
-        if edge_order > 2:
-            raise ValueError("'edge_order' greater than 2 not supported")
-        t_span = abs(float(t[-1]) - float(t[0]))
-        if t_span == 0.0:
-            raise ZeroDivisionError("float division by zero")  # R:lagrangian.py:71
-        eng = Engine.get()
+        """Multi-GPU with ``sharding.set_host_result("shared")``: this rank's slab goes through
+        the same chunk pipeline straight into the host segment all ranks of the box map - no
+        device all-gather, the field crosses PCIe once in total, and the copies (bounded by the
+        box's aggregate device-to-host bandwidth, ~100 GB/s for 8 GPUs) hide behind K1.  The
+        one or two halo rows are integrated locally (bit-identical to the neighbours' rows), so
+        chunks do not wait for other ranks.  ``flow_map`` / ``field_device`` hold this rank's
+        rows only."""
+        plan = self._plan(x, y, f, t, kwargs)
+        rank, size = sharding.world()
+        slab = sharding.partition(self.ydim, size, rank)
         host_np, host_t = sharding.shared_host_array((self.ydim, self.xdim))
         own = None
+        self._counters_pending, self._counter_tensors = False, None
         if slab.rows:
-            own, _ = eng.ftle_stencil(local, slab.lo, self._xf, self._yf, edge_order, t_span,
-                                      slab.row0, slab.rows, nat.XI_NONE)
-            host_t[slab.row0:slab.row0 + slab.rows].copy_(own, non_blocking=True)
-        torch.cuda.current_stream(eng.device).synchronize()
-        torch.distributed.barrier()  # every rank's rows are in the segment
+            fm, own = self._pipeline(plan, t, edge_order, slab.lo, slab.hi, slab.row0,
+                                     slab.row0 + slab.rows, host_t)
+            self.flow_map = fm[slab.halo_lo:slab.halo_lo + slab.rows]
+        else:
+            if edge_order > 2:
+                raise ValueError("'edge_order' greater than 2 not supported")
+            if float(t[-1]) == float(t[0]):
+                raise ZeroDivisionError("float division by zero")  # R:lagrangian.py:71
+        sharding.host_barrier()  # every rank's rows are in the segment
         self.field_device = own
         self.field = np.ma.MaskedArray(host_np)
         self._collect_stats()

@@ -31,6 +31,37 @@ def set_distributed(mode) -> None:
 _halo = "exchange"
 
 
+_barrier_state = None  # (flags ndarray over shared memory, generation)
+
+
+def host_barrier(timeout_s: float = 120.0) -> None:
+    """Barrier between the ranks of the box through a few words of shared memory (a store and a
+    spin on the host, ~10 us) instead of a device collective: the shared-result path has nothing
+    left to exchange on the device, and an NCCL barrier costs a kernel launch plus a device
+    synchronisation on every rank.  Every rank must already have synchronised the stream whose
+    copies the others are going to read."""
+    global _barrier_state
+    rank, size = world()
+    if size == 1:
+        return
+    if _barrier_state is None:
+        flags, _ = shared_host_array((max(size, 8),), dtype=np.int64, tag="barrier")
+        dist.barrier()  # rank 0 zero-filled the segment before anybody counts on it
+        _barrier_state = [flags, 0]
+    flags = _barrier_state[0]
+    _barrier_state[1] += 1
+    gen = _barrier_state[1]
+    flags[rank] = gen
+    import time
+
+    deadline = time.monotonic() + timeout_s
+    spins = 0
+    while int(flags[:size].min()) < gen:
+        spins += 1
+        if spins & 0x3ff == 0 and time.monotonic() > deadline:
+            raise RuntimeError("host_barrier: a rank did not arrive (died or never called it)")
+
+
 def set_halo_mode(mode) -> None:
     """How a rank obtains the flow-map rows just outside its slab that the stencil needs:
     ``"exchange"``: one row from each neighbour (``exchange_halo``); ``"redundant"``: integrate
@@ -74,10 +105,10 @@ def host_result_shared() -> bool:
     return _host_result == "shared" and world()[1] > 1
 
 
-_segments = {}  # nbytes -> (mmap object, flat uint8 ndarray)
+_segments = {}  # (tag, nbytes) -> (mmap object, flat uint8 ndarray)
 
 
-def shared_host_array(shape, dtype=np.float64):
+def shared_host_array(shape, dtype=np.float64, tag="result"):
     """Collective over the default process group: a host array of ``shape`` backed by one
     POSIX shared-memory segment mapped by every rank of the box (page-locked for CUDA when a
     device is in use, so slab copies into it run at PCIe speed).  Segments are cached by size
@@ -85,7 +116,8 @@ def shared_host_array(shape, dtype=np.float64):
     nothing is left in /dev/shm whatever happens to the job afterwards."""
     rank, size = world()
     nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-    seg = _segments.get(nbytes)
+    key = (tag, nbytes)
+    seg = _segments.get(key)
     if seg is None:
         hosts = [None] * size
         dist.all_gather_object(hosts, socket.gethostname())
@@ -110,7 +142,7 @@ def shared_host_array(shape, dtype=np.float64):
         if torch.cuda.is_available() and dist.get_backend() == "nccl":
             torch.cuda.check_error(
                 torch.cuda.cudart().cudaHostRegister(flat.ctypes.data, max(nbytes, 1), 0))
-        seg = _segments[nbytes] = (mm, flat)
+        seg = _segments[key] = (mm, flat)
     arr = seg[1][:nbytes].view(dtype).reshape(shape)
     return arr, torch.from_numpy(arr)
 

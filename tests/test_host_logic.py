@@ -268,8 +268,20 @@ def _shared_worker(rank, size, port, out_dir):
             dist.barrier()
         assert len(sharding._segments) == 1
         assert not [n for n in os.listdir("/dev/shm") if n.startswith("dynlab_b200_")]
+        # host_barrier: nobody leaves before everybody has arrived, generation after generation
+        import time
+        for gen in range(5):
+            if rank == gen % size:
+                time.sleep(0.05)
+            arr[0, 0] = -1.0 if rank == 0 else arr[0, 0]
+            stamp, _ = sharding.shared_host_array((size,), tag="stamps")
+            stamp[rank] = gen + 1
+            sharding.host_barrier()
+            assert (stamp >= gen + 1).all()
+            sharding.host_barrier()
+        n_before = len(sharding._segments)
         other, _ = sharding.shared_host_array((3, 5))
-        assert other.shape == (3, 5) and len(sharding._segments) == 2
+        assert other.shape == (3, 5) and len(sharding._segments) == n_before + 1
         sharding.set_host_result("all")
         assert not sharding.host_result_shared()
         with pytest.raises(ValueError):
