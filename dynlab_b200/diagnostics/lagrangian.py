@@ -43,6 +43,30 @@ def _ftle_on_device(diag, local, slab, t, edge_order, xi_mode):
     return field, xi
 
 
+def pipeline_schedule(lo, hi, own0, own1, ydim, edge_order, chunks, last_fraction):
+    """Chunk plan of ``FTLE._pipeline``: a list of ``(r0, r1, done, upto)`` - integrate global rows
+    [r0, r1), then produce the FTLE rows [done, upto) (empty when ``upto == done``).  The chunks
+    tile [lo, hi) in order (equal chunks and a short last one, whose copy is the only one left
+    exposed; small slabs: one chunk), the output ranges tile [own0, own1) in order, and every
+    row an output row's stencil reads - its neighbours, and rows 0..2 / ydim-3..ydim-1 for the
+    one-sided edge_order-2 formulas at the global edges - lies in [lo, r1)."""
+    nloc = hi - lo
+    if chunks > 1 and nloc >= 64 * chunks:
+        last = max(64, nloc // last_fraction)
+        bounds = [lo + (nloc - last) * c // (chunks - 1) for c in range(chunks)] + [hi]
+    else:
+        bounds = [lo, hi]
+    steps, done = [], own0
+    for r0, r1 in zip(bounds[:-1], bounds[1:]):
+        upto = own1 if r1 == hi else min(own1, r1 - 1)  # row r1-1 still needs row r1
+        if done == 0 and edge_order == 2 and r1 < min(3, ydim):
+            upto = done  # the one-sided formula of row 0 reads rows 0..2
+        upto = max(upto, done)
+        steps.append((r0, r1, done, upto))
+        done = upto
+    return steps
+
+
 class FTLE(LagrangianDiagnostic2D):
     """Finite-time Lyapunov exponent field of a 2-D flow (R:lagrangian.py:9-78)."""
 
@@ -88,25 +112,15 @@ class FTLE(LagrangianDiagnostic2D):
         if t_span == 0.0:
             raise ZeroDivisionError("float division by zero")  # R:lagrangian.py:71
         eng = Engine.get()
-        n, nloc, xdim = self.pipeline_chunks, hi - lo, self.xdim
-        if n > 1 and nloc >= 64 * n:
-            # equal chunks except a short last one: only its device-to-host copy is left exposed
-            last = max(64, nloc // self.pipeline_last_fraction)
-            bounds = [lo + (nloc - last) * c // (n - 1) for c in range(n)] + [hi]
-        else:  # small slab: one chunk
-            n, bounds = 1, [lo, hi]
+        nloc, xdim = hi - lo, self.xdim
+        steps = pipeline_schedule(lo, hi, own0, own1, self.ydim, edge_order, self.pipeline_chunks,
+                                  self.pipeline_last_fraction)
         fm = eng.empty(nloc, xdim, 2)
         field = eng.empty(max(own1 - own0, 1), xdim)
-        counters = torch.zeros(n, nat.CNT_WORDS, dtype=torch.int64, device=eng.device)
+        counters = torch.zeros(len(steps), nat.CNT_WORDS, dtype=torch.int64, device=eng.device)
         main = torch.cuda.current_stream(eng.device)
-        done = own0  # FTLE rows [own0, done) are already produced
-        for c in range(n):
-            r0, r1 = bounds[c], bounds[c + 1]
-            if r1 > r0:
-                self._integrate_rows(plan, r0, r1 - r0, fm[r0 - lo:r1 - lo], counters=counters[c])
-            upto = own1 if r1 == hi else min(own1, r1 - 1)  # row r1-1 still needs row r1
-            if done == 0 and edge_order == 2 and r1 < min(3, hi):
-                upto = done  # the one-sided formula of row 0 reads rows 0..2
+        for c, (r0, r1, done, upto) in enumerate(steps):
+            self._integrate_rows(plan, r0, r1 - r0, fm[r0 - lo:r1 - lo], counters=counters[c])
             if upto > done:
                 eng.ftle_stencil(fm[:r1 - lo], lo, self._xf, self._yf, edge_order, t_span, done,
                                  upto - done, out=field[done - own0:upto - own0])
@@ -115,7 +129,6 @@ class FTLE(LagrangianDiagnostic2D):
                 eng.copy_stream.wait_event(ev)
                 with torch.cuda.stream(eng.copy_stream):
                     host[done:upto].copy_(field[done - own0:upto - own0], non_blocking=True)
-                done = upto
         eng.copy_stream.synchronize()
         field.record_stream(eng.copy_stream)
         self._counters_pending, self._counter_tensors = True, counters

@@ -343,3 +343,38 @@ def test_ctypes_signatures_match_header_arity():
         params = " ".join(params.split())
         n = 0 if params in ("", "void") else params.count(",") + 1
         assert n == len(_native.SIGNATURES[name][1]), (name, n, len(_native.SIGNATURES[name][1]))
+
+
+def test_pipeline_schedule_invariants():
+    """FTLE._pipeline's chunk plan (single GPU: the whole grid; multi-GPU shared mode: a slab with
+    locally integrated halo rows): chunks tile [lo, hi), output ranges tile [own0, own1), and
+    every row a stencil reads has been integrated when its output range is produced."""
+    from dynlab_b200.diagnostics.lagrangian import pipeline_schedule
+    from dynlab_b200.sharding import partition
+
+    def check(lo, hi, own0, own1, ydim, eo, chunks, frac):
+        steps = pipeline_schedule(lo, hi, own0, own1, ydim, eo, chunks, frac)
+        assert steps[0][0] == lo and steps[-1][1] == hi
+        assert all(a[1] == b[0] for a, b in zip(steps, steps[1:]))      # chunks tile [lo, hi)
+        assert all(r1 > r0 for r0, r1, _, _ in steps)
+        assert steps[0][2] == own0 and steps[-1][3] == own1
+        assert all(a[3] == b[2] for a, b in zip(steps, steps[1:]))      # outputs tile [own0, own1)
+        for _, r1, done, upto in steps:
+            if upto == done:
+                continue
+            need_lo, need_hi = max(done - 1, 0), min(upto, ydim - 1)     # neighbours
+            if eo == 2 and done == 0:
+                need_hi = max(need_hi, min(2, ydim - 1))                  # one-sided, top edge
+            if eo == 2 and upto == ydim:
+                need_lo = min(need_lo, max(ydim - 3, 0))                  # one-sided, bottom edge
+            assert lo <= need_lo and need_hi < r1, (lo, hi, own0, own1, ydim, eo, done, upto, r1)
+
+    for ydim in (3, 4, 5, 63, 64, 255, 256, 257, 1000, 4096):
+        for eo in (1, 2):
+            for chunks, frac in ((4, 32), (1, 32), (2, 16), (8, 64)):
+                check(0, ydim, 0, ydim, ydim, eo, chunks, frac)           # single GPU
+                for size in (2, 3, 8):
+                    for rank in range(size):
+                        s = partition(ydim, size, rank)
+                        if s.rows:
+                            check(s.lo, s.hi, s.row0, s.row0 + s.rows, ydim, eo, chunks, frac)
