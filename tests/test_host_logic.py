@@ -378,3 +378,27 @@ def test_pipeline_schedule_invariants():
                         s = partition(ydim, size, rank)
                         if s.rows:
                             check(s.lo, s.hi, s.row0, s.row0 + s.rows, ydim, eo, chunks, frac)
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line
+    with the contract's keys; it needs no GPU."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--gpus", "1", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "seeds/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("FTLE seeds/sec") and line["value"] > 0
+    assert line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 0
+    assert line["dtype"] == "f64" and line["data"] == "synthetic" and "workload" in line["config"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"]
+    assert abs(cb["value"] - line["value"]) <= 1e-9 * line["value"]
+    e2e = line["e2e"]
+    assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+    assert e2e["unit"] == line["unit"] and abs(e2e["value"] - line["value"]) <= 1e-9 * line["value"]
