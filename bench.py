@@ -330,7 +330,8 @@ def run_ours(args):
                     "note": "public API FTLE().compute: host coordinates in, full host field out "
                             "on EVERY rank (N=1: pinned D2H overlapped with K1 in row chunks; N>1: "
                             "sharding.set_host_result('shared'), one pinned host segment mapped by "
-                            "all ranks, each rank copies its own rows)",
+                            "all ranks, each rank streams its own rows into it through the same "
+                            "chunk pipeline, halo rows integrated locally)",
                     "private_copy_per_rank_ms_per_step": None if e2e_all_s is None else e2e_all_s * 1e3,
                     "rank0_host_only_ms_per_step": None if e2e_rank0_s is None else e2e_rank0_s * 1e3},
             "gpu_launches": launches,
