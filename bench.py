@@ -142,36 +142,86 @@ def cpu_baseline_c_port(target_s: float = 12.0):
                       f"{cores} threads", "mean_nfev": float(nfev.mean())}
 
 
-def reference_python_port(seeds_target: int, integrator: str = "lsoda"):
-    """The reference's own algorithm, restated in oracle/py_oracle.py: per-seed scipy solve
-    through a process pool over all cores (R:_base_classes.py:139-148,178-185), then
-    np.gradient and the per-point eig loop (R:lagrangian.py:50-76)."""
-    from oracle import py_oracle as po
+def workload_config(world: int) -> dict:
+    """`config` of the JSON line: identical for our arm and the reference arm."""
+    return {"workload": "FTLE double_gyre 8192x4096, t=(10,0), edge_order=2, rtol=atol=1e-8 "
+                        "(BASELINE configs[2])",
+            "grid": [XDIM, YDIM], "t": list(T_SPAN), "edge_order": EDGE_ORDER, "rtol": TOL,
+            "atol": TOL, "n_gpus": world,
+            "l2": "inputs/outputs (537 MB flow map + 268 MB field per step) exceed the 126 MB "
+                  "L2; no flush needed"}
 
-    cores = host_cores()
+
+def sample_grid(seeds_target: int):
+    """Strided sub-grid of config 3 (same domain, every stride-th row and column) with at least
+    ``seeds_target`` seeds."""
     stride = 64
     while stride > 1 and (XDIM // stride) * (YDIM // stride) < seeds_target:
         stride //= 2
     x, y = grid(stride)
-    integ = po.odeint_wrapper if integrator == "lsoda" else po.rk45_wrapper
-    f = po.FlowSpec("double_gyre")
-    t0 = time.perf_counter()
-    fm = po.flow_map(x, y, f, T_SPAN, integrator=integ, num_threads=cores, rtol=TOL, atol=TOL)
-    po.ftle_from_flow_map(fm, x, y, T_SPAN, EDGE_ORDER)
-    dt = time.perf_counter() - t0
+    return x, y, (f"every {stride}th row and column of the 8192x4096 grid "
+                  f"({x.size}x{y.size} = {x.size * y.size} seeds)")
+
+
+def reference_ftle(seeds_target: int, integrator: str = "lsoda"):
+    """One `FTLE(num_threads=cores).compute(...)` of the reference on a strided sample of config 3.
+
+    With oracle/_ref present (oracle/build_ref.sh) this is the UNMODIFIED reference package:
+    `dynlab.diagnostics.FTLE` (R:lagrangian.py:23-78) with its default integrator (scipy LSODA,
+    R:utils.py:23-25) or the scipy RK45 wrapper passed through its `integrator=` argument, its own
+    process pool over all cores (R:_base_classes.py:139-146), np.gradient and np.linalg.eig loop.
+    Without it (kind "port") the same steps restated in oracle/py_oracle.py.
+    Returns (seeds/s, seconds, sample description, cores, kind, what)."""
+    from oracle import ref_loader
+
+    cores = host_cores()
+    x, y, sample = sample_grid(seeds_target)
+    if ref_loader.reference_available():
+        ref_loader.load_reference()
+        from dynlab.diagnostics import FTLE as RefFTLE
+        from dynlab.flows import double_gyre as ref_double_gyre
+
+        kw = {} if integrator == "lsoda" else {"integrator": ref_loader.rk45_wrapper}
+        t0 = time.perf_counter()
+        d = RefFTLE(num_threads=cores, **kw)
+        field = d.compute(x, y, ref_double_gyre, T_SPAN, edge_order=EDGE_ORDER, rtol=TOL, atol=TOL)
+        dt = time.perf_counter() - t0
+        assert field.shape == (y.size, x.size)
+        kind = "reference"
+        what = ("unmodified hokiepete/dynlab from oracle/_ref: dynlab.diagnostics.FTLE("
+                f"num_threads={cores}).compute, "
+                + ("default integrator (scipy odeint / LSODA)" if integrator == "lsoda"
+                   else "integrator = scipy solve_ivp RK45 wrapper")
+                + ", its own process pool + np.gradient + np.linalg.eig loop")
+    else:
+        from oracle import py_oracle as po
+
+        integ = po.odeint_wrapper if integrator == "lsoda" else po.rk45_wrapper
+        t0 = time.perf_counter()
+        fm = po.flow_map(x, y, po.FlowSpec("double_gyre"), T_SPAN, integrator=integ,
+                         num_threads=cores, rtol=TOL, atol=TOL)
+        po.ftle_from_flow_map(fm, x, y, T_SPAN, EDGE_ORDER)
+        dt = time.perf_counter() - t0
+        kind = "port"
+        what = ("oracle/_ref absent (oracle/build_ref.sh was not run where /root/reference "
+                "exists): oracle/py_oracle.py restatement, scipy "
+                + ("odeint (LSODA)" if integrator == "lsoda" else "solve_ivp RK45")
+                + " per seed through a process pool + np.gradient + np.linalg.eig")
     n = x.size * y.size
-    return n / dt, dt, f"every {stride}th row and column of the 8192x4096 grid ({x.size}x{y.size} = {n} seeds)", cores
+    return n / dt, dt, sample, cores, kind, what
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     cores = host_cores()
-    times, sample, n_seeds = [], "", 0
-    target = max(2048, 600 * cores)
+    times, n_seeds = [], 0
+    target = args.ref_seeds or max(2048, 600 * cores)
+    sample = kind = what = ""
     for i in range(args.warmup + args.steps):
-        v, dt, sample, cores = reference_python_port(target)
+        v, dt, sample, cores, kind, what = reference_ftle(target, args.ref_integrator)
         if i >= args.warmup:
             times.append(dt)
             n_seeds = v * dt
@@ -181,18 +231,26 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "seeds/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": "FTLE double_gyre 8192x4096, t=(10,0), edge_order=2, "
-                               "rtol=atol=1e-8 (BASELINE configs[2]); each step = " + sample},
-        "cpu_baseline": {"value": value, "unit": "seeds/s", "cores": cores, "kind": "port",
-                         "sample": sample + "; oracle/py_oracle.py: scipy odeint (LSODA, the "
-                                   "reference's default integrator) per seed through a process "
-                                   "pool over all cores + np.gradient + np.linalg.eig"},
+        "data": "synthetic", "config": workload_config(world),
+        "cpu_baseline": {"value": value, "unit": "seeds/s", "cores": cores, "kind": kind,
+                         "sample": "each step = " + sample + "; " + what},
         "e2e": {"value": value, "unit": "seeds/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def reference_subprocess(seeds: int, integrator: str, steps: int = 1):
+    """The reference arm in a fresh interpreter (its process pool forks; this process holds a
+    CUDA context).  Returns the parsed JSON line."""
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference",
+                          "--steps", str(steps), "--warmup", "0", "--ref-seeds", str(seeds),
+                          "--ref-integrator", integrator], env=env, check=True,
+                         capture_output=True, text=True, timeout=900).stdout
+    return json.loads(out.strip().splitlines()[-1])
 
 
 # ------------------------------------------------------------------------- GPU arm
@@ -379,6 +437,10 @@ def main():
     ap.add_argument("--halo", choices=["exchange", "redundant"], default=None,
                     help="multi-GPU: how ranks obtain the halo rows (default: the library's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-seeds", type=int, default=0,
+                    help="--impl reference: seeds per step (default 600 per host core)")
+    ap.add_argument("--ref-integrator", choices=["lsoda", "rk45"], default="lsoda",
+                    help="--impl reference: the reference's default integrator or scipy RK45")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

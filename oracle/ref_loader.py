@@ -1,10 +1,15 @@
-"""TEST INFRASTRUCTURE — loader for the real hokiepete/dynlab reference.
+"""TEST / BENCH INFRASTRUCTURE — loader for the real, unmodified hokiepete/dynlab reference.
 
-Only usable where ``/root/reference`` exists (the build container).  Nothing in
-``-m gpu`` tests, ``smoke()`` or ``bench.py`` may import this module: the GPU box
-has no reference tree.  It is used by ``oracle/make_golden.py`` to generate the
-fixtures under ``tests/golden/`` and by ``tests/test_oracle_vs_reference.py``
-(skipped when the tree is absent) to pin ``oracle/py_oracle.py``.
+Two places can hold the reference package:
+
+* ``oracle/_ref/dynlab`` — the byte-for-byte copy made by ``oracle/build_ref.sh`` (git-ignored,
+  travels to the GPU box with the gpurun snapshot; ``SHA256SUMS`` beside it records what was
+  copied).  This is what ``bench.py --impl reference`` and the ``cpu_baseline`` leg time.
+* ``/root/reference/src`` — the read-only tree of the build container, used by
+  ``oracle/make_golden.py`` to generate the fixtures under ``tests/golden/`` and by
+  ``tests/test_oracle_golden.py::test_oracle_vs_live_reference`` (skipped when neither exists).
+
+Nothing in ``dynlab_b200/`` imports this module; the product never runs reference code.
 
 The reference imports ``contourpy`` and ``pathos`` at module scope
 (/root/reference/src/dynlab/diagnostics/_base_classes.py:7-8); neither is in
@@ -22,11 +27,24 @@ import os
 import sys
 import types
 
-REFERENCE_SRC = "/root/reference/src"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_COPY = os.path.join(_HERE, "_ref")           # oracle/build_ref.sh
+REFERENCE_TREE = "/root/reference/src"           # build container only
+
+
+def reference_root():
+    """Directory to put on sys.path for ``import dynlab`` (the travelling copy first), or None."""
+    for root in (REF_COPY, REFERENCE_TREE):
+        if os.path.isfile(os.path.join(root, "dynlab", "diagnostics", "lagrangian.py")):
+            return root
+    return None
+
+
+REFERENCE_SRC = reference_root() or REFERENCE_TREE
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_SRC, "dynlab"))
+    return reference_root() is not None
 
 
 def _install_shims() -> None:
@@ -61,11 +79,18 @@ def _install_shims() -> None:
 
 def load_reference():
     """Return the unmodified reference package ``dynlab`` (with diagnostics)."""
-    if not reference_available():
-        raise RuntimeError("reference tree not present at " + REFERENCE_SRC)
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference package not found: run oracle/build_ref.sh where "
+                           "/root/reference exists")
+    mod = sys.modules.get("dynlab")
+    if mod is not None and not (getattr(mod, "__file__", "") or "").startswith(root):
+        raise RuntimeError("`dynlab` is already imported from somewhere else "
+                           f"({getattr(mod, '__file__', None)}): dynlab_b200.install_as_dynlab() "
+                           "and the real reference cannot share a process")
     _install_shims()
-    if REFERENCE_SRC not in sys.path:
-        sys.path.insert(0, REFERENCE_SRC)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import dynlab  # noqa: F401
     import dynlab.diagnostics  # noqa: F401
     import dynlab.flows  # noqa: F401

@@ -229,3 +229,54 @@ def test_c_gradient_matches_numpy():
                     gy, gx = np.gradient(f, y, x, edge_order=eo)
                     cy, cx = co.gradient(f, y, x, eo)
                     assert np.array_equal(gy, cy) and np.array_equal(gx, cx)
+
+
+# ---------------- (3) the live reference (oracle/_ref or /root/reference), when present ----------------
+_LIVE = r"""
+import json, sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from oracle import ref_loader, py_oracle as po
+ref_loader.load_reference()
+from dynlab.diagnostics import FTLE, AttractionRate
+from dynlab.flows import double_gyre, bickley_jet
+x, y = np.linspace(0, 2, 9), np.linspace(0, 1, 6)
+out = {}
+for name, integ, pint in (("lsoda", None, po.odeint_wrapper), ("rk45", ref_loader.rk45_wrapper, po.rk45_wrapper)):
+    d = FTLE(num_threads=2, **({} if integ is None else {"integrator": integ}))
+    ref = d.compute(x, y, double_gyre, (3, 0), edge_order=2, rtol=1e-8, atol=1e-8)
+    mine, fm = po.ftle(x, y, po.flow("double_gyre"), (3, 0), edge_order=2, integrator=pint, rtol=1e-8, atol=1e-8)
+    out[name] = [bool(np.array_equal(np.ma.getdata(ref), np.ma.getdata(mine))), bool(np.array_equal(d.flow_map, fm))]
+xe, ye = np.linspace(0, 20, 12), np.linspace(-4, 4, 7)
+u, v = bickley_jet(0, np.meshgrid(xe, ye))
+ref = AttractionRate().compute(xe, ye, u=u, v=v, edge_order=2)
+mine = po.attraction_repulsion_rate(xe, ye, u=u, v=v, edge_order=2, eigenvalue_index=0)
+out["attraction"] = [bool(np.array_equal(np.ma.getdata(ref), np.ma.getdata(mine)))]
+print(json.dumps(out))
+"""
+
+
+def test_oracle_vs_live_reference():
+    """py_oracle against the unmodified reference package itself (fresh interpreter: the GPU
+    tests register dynlab_b200 under the name `dynlab` in this one)."""
+    import hashlib
+    import json
+    import os
+    import subprocess
+    import sys
+
+    from oracle import ref_loader
+
+    root = ref_loader.reference_root()
+    if root is None:
+        pytest.skip("no reference package here (oracle/build_ref.sh not run)")
+    sums = os.path.join(ref_loader.REF_COPY, "SHA256SUMS")
+    if root == ref_loader.REF_COPY and os.path.exists(sums):
+        for line in open(sums):  # the travelling copy is what build_ref.sh copied, unmodified
+            digest, rel = line.split()
+            assert hashlib.sha256(open(os.path.join(root, rel), "rb").read()).hexdigest() == digest
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", _LIVE, repo], capture_output=True, text=True,
+                         timeout=600, cwd=repo)
+    assert res.returncode == 0, res.stderr[-2000:]
+    out = json.loads(res.stdout.strip().splitlines()[-1])
+    assert out == {"lsoda": [True, True], "rk45": [True, True], "attraction": [True]}, out
