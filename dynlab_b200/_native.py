@@ -47,7 +47,22 @@ SIGNATURES = {
     "dlb_select_scratch_bytes": (_sz, []),
     "dlb_order_statistics": (_i, [_vp, _i64, C.POINTER(C.c_int64), _i, _vp, _vp, _vp, _sz, _vp]),
     "dlb_dfma_peak": (_i, [_i, _dp, _dp]),
+    # multi-GPU helpers (csrc/peer.cu)
+    "dlb_device_count": (_i, [C.POINTER(C.c_int)]),
+    "dlb_peer_enable": (_i, [_i, _i]),
+    "dlb_peer_alloc": (_i, [_sz, C.POINTER(_vp)]),
+    "dlb_peer_free": (_i, [_vp]),
+    "dlb_ipc_export": (_i, [_vp, C.c_char_p]),
+    "dlb_ipc_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "dlb_ipc_close": (_i, [_vp]),
+    "dlb_peer_copy": (_i, [_vp, _vp, _sz, _vp]),
+    "dlb_gather_rows": (_i, [_vp, _sz, C.POINTER(_vp), _i, C.POINTER(_vp), C.c_uint64, _vp]),
+    "dlb_halo_exchange": (_i, [_vp, _sz, _i64, _i64, _vp, _vp, _vp, _vp, C.c_uint64, _vp]),
+    "dlb_wait_flags": (_i, [_vp, _i, C.c_uint64, _d, _vp, _vp]),
 }
+
+MAX_PEERS = 16
+IPC_HANDLE_BYTES = 64
 
 
 class NativeLibraryMissing(ImportError):

@@ -8,6 +8,8 @@
 #include "../../include/dynlab_b200.h"
 
 #define DLB_MAX_CONSTS 16
+#define DLB_MAX_DEVICES 64  // per-device tables (power of two)
+#define DLB_AXES_ENTRIES 16 // stencil coefficient cache: workspaces kept warm
 
 // Flow parameters after host-side preparation (flows.cuh: flow_prepare).  Passed to
 // kernels by value, so every thread reads them from the constant bank.

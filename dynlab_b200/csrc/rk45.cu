@@ -416,20 +416,23 @@ __global__ void __launch_bounds__(RK_BLOCK, DLB_RK_MINBLOCKS) rk45_kernel(const 
   }
 }
 
-int g_num_sms = 0;
-
 template <int ID, int N, bool GRID>
 int launch_rk45(const Rk45Params& P, cudaStream_t stream) {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    DLB_CUDA_CHECK(cudaGetDevice(&dev));
-    DLB_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  // per device and kernel instance: SM count x resident CTAs per SM (one process may drive
+  // several devices)
+  static int resident_of[DLB_MAX_DEVICES] = {0};
+  int dev = 0;
+  DLB_CUDA_CHECK(cudaGetDevice(&dev));
+  int& resident = resident_of[dev & (DLB_MAX_DEVICES - 1)];
+  if (resident == 0) {
+    int sms = 0, per_sm = 0;
+    DLB_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    DLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &per_sm, rk45_kernel<ID, N, GRID>, RK_BLOCK, 0));
+    if (per_sm < 1) per_sm = 1;
+    resident = sms * per_sm;
   }
-  int per_sm = 0;
-  DLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rk45_kernel<ID, N, GRID>,
-                                                               RK_BLOCK, 0));
-  if (per_sm < 1) per_sm = 1;
-  long long blocks = (long long)g_num_sms * per_sm;
+  long long blocks = resident;
   const long long needed = (P.total + RK_BLOCK - 1) / RK_BLOCK;
   if (blocks > needed) blocks = needed;
   if (blocks < 1) blocks = 1;

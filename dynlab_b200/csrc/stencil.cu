@@ -46,15 +46,16 @@ int env_flag(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-int g_sms = 0;
+// SM count of the CURRENT device (one process may drive several devices: per-device table)
 int num_sms() {
-  if (g_sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      g_sms = 148;
-  }
-  return g_sms;
+  static int sms_of[DLB_MAX_DEVICES] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int& sms = sms_of[dev & (DLB_MAX_DEVICES - 1)];
+  if (sms == 0 &&
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    sms = 148;
+  return sms;
 }
 
 }  // namespace dlbst
@@ -586,10 +587,10 @@ int launch_tma(const StencilParams& P, const CUtensorMap& m0, const CUtensorMap&
                long long ntasks, cudaStream_t stream) {
   auto kern = stencil_tma_kernel<KIND, MODE, XI, AOS>;
   constexpr int dyn = TM_STAGES * TM_STAGE_BYTES;
-  static int per_sm_of[64] = {0};  // per device: the attribute is a per-device setting
+  static int per_sm_of[DLB_MAX_DEVICES] = {0};  // the attribute is a per-device setting
   int dev = 0;
   DLB_CUDA_CHECK(cudaGetDevice(&dev));
-  int& per_sm = per_sm_of[dev & 63];
+  int& per_sm = per_sm_of[dev & (DLB_MAX_DEVICES - 1)];
   if (per_sm == 0) {
     DLB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     DLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TM_THREADS, dyn));
@@ -602,14 +603,15 @@ int launch_tma(const StencilParams& P, const CUtensorMap& m0, const CUtensorMap&
   return DLB_OK;
 }
 
-// (fl(1/c), -ln(fl(1/c))) for c = 1 + i/128, uploaded once per process and device.
+// (fl(1/c), -ln(fl(1/c))) for c = 1 + i/128, uploaded once per device (a __device__ symbol has
+// one instance per device).
 int ensure_logtab() {
   static std::mutex mu;
-  static int done_dev = -1;
+  static bool done[DLB_MAX_DEVICES] = {false};
   std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   DLB_CUDA_CHECK(cudaGetDevice(&dev));
-  if (done_dev == dev) return DLB_OK;
+  if (done[dev & (DLB_MAX_DEVICES - 1)]) return DLB_OK;
   double2 h[128];
   for (int i = 0; i < 128; ++i) {
     const double c = 1.0 + i / 128.0;
@@ -618,7 +620,7 @@ int ensure_logtab() {
     h[i].y = (i == 0) ? 0.0 : (double)(-logl((long double)inv));
   }
   DLB_CUDA_CHECK(cudaMemcpyToSymbol(g_logtab, h, sizeof(h)));
-  done_dev = dev;
+  done[dev & (DLB_MAX_DEVICES - 1)] = true;
   return DLB_OK;
 }
 
@@ -804,15 +806,36 @@ void build_axis(const double* c, long long n, int edge_order, HostAxis* H) {
   }
 }
 
-// Last (workspace, x, y, edge_order) whose coefficients are resident in the workspace.
-struct AxesCache {
-  std::mutex mu;
+// (x, y, edge_order) whose coefficients are resident in a workspace, one entry per workspace
+// (= per device / engine; a process that drives several devices keeps all of them warm).
+struct AxesEntry {
   bool valid = false;
   const void* ws = nullptr;
+  int device = -1;
   int edge_order = 0;
   std::vector<double> x, y;
   HostAxis hx, hy;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // stream of the upload / the last user
+  cudaEvent_t uploaded = nullptr;  // recorded after the upload (owned by the entry)
+  unsigned long long tick = 0;
+};
+struct AxesCache {
+  std::mutex mu;
+  AxesEntry e[DLB_AXES_ENTRIES];
+  unsigned long long clock = 0;
+  AxesEntry* find(const void* ws) {
+    for (auto& a : e)
+      if (a.ws == ws) return &a;
+    return nullptr;
+  }
+  AxesEntry* victim() {  // an unused slot, else the least recently used one
+    AxesEntry* v = &e[0];
+    for (auto& a : e) {
+      if (!a.ws) return &a;
+      if (a.tick < v->tick) v = &a;
+    }
+    return v;
+  }
 };
 AxesCache& axes_cache() {
   static AxesCache c;
@@ -852,14 +875,33 @@ int setup_axes(StencilParams& P, const double* h_x, int64_t xdim, const double* 
   double* base = (double*)((char*)d_workspace + 256) + (xdim + ydim);
   double* dxa = base;
   double* dya = base + 3 * xdim;
-  AxesCache& cache = axes_cache();
-  std::lock_guard<std::mutex> lock(cache.mu);
-  const bool hit = cache.valid && cache.ws == d_workspace && cache.edge_order == edge_order &&
-                   (int64_t)cache.x.size() == xdim && (int64_t)cache.y.size() == ydim &&
-                   memcmp(cache.x.data(), h_x, sizeof(double) * xdim) == 0 &&
-                   memcmp(cache.y.data(), h_y, sizeof(double) * ydim) == 0;
+  AxesCache& all = axes_cache();
+  std::lock_guard<std::mutex> lock(all.mu);
+  int dev = 0;
+  DLB_CUDA_CHECK(cudaGetDevice(&dev));
+  AxesEntry* found = all.find(d_workspace);
+  const bool hit = found && found->valid && found->device == dev &&
+                   found->edge_order == edge_order && (int64_t)found->x.size() == xdim &&
+                   (int64_t)found->y.size() == ydim &&
+                   memcmp(found->x.data(), h_x, sizeof(double) * xdim) == 0 &&
+                   memcmp(found->y.data(), h_y, sizeof(double) * ydim) == 0;
+  AxesEntry& cache = found ? *found : *all.victim();
+  cache.tick = ++all.clock;
   if (!hit) {
+    if (found && found->stream != stream && found->device == dev) {
+      // kernels enqueued on another stream may still read the coefficients this upload is
+      // about to overwrite; their completion cannot be observed from here (the stream handle
+      // may even be gone), so drain the device.  Rare: same workspace, new grid, new stream.
+      DLB_CUDA_CHECK(cudaDeviceSynchronize());
+    }
+    if (cache.uploaded && cache.device != dev) {  // slot reused for another device
+      cudaEventDestroy(cache.uploaded);
+      (void)cudaGetLastError();
+      cache.uploaded = nullptr;
+    }
     cache.valid = false;
+    cache.ws = d_workspace;
+    cache.device = dev;
     build_axis(h_x, xdim, edge_order, &cache.hx);
     build_axis(h_y, ydim, edge_order, &cache.hy);
     const HostAxis &hx = cache.hx, &hy = cache.hy;
@@ -882,15 +924,18 @@ int setup_axes(StencilParams& P, const double* h_x, int64_t xdim, const double* 
     // pageable source: cudaMemcpyAsync stages it before returning, so `stage` may die here
     DLB_CUDA_CHECK(cudaMemcpyAsync(base, stage.data(), sizeof(double) * stage.size(),
                                    cudaMemcpyHostToDevice, stream));
-    cache.ws = d_workspace;
+    if (!cache.uploaded)
+      DLB_CUDA_CHECK(cudaEventCreateWithFlags(&cache.uploaded, cudaEventDisableTiming));
+    DLB_CUDA_CHECK(cudaEventRecord(cache.uploaded, stream));
     cache.edge_order = edge_order;
     cache.x.assign(h_x, h_x + xdim);
     cache.y.assign(h_y, h_y + ydim);
     cache.stream = stream;
     cache.valid = true;
   } else if (cache.stream != stream) {
-    // uploaded on another stream: order this stream after it
-    DLB_CUDA_CHECK(cudaStreamSynchronize(cache.stream));
+    // uploaded on another stream: order this stream after the upload (device-side wait on the
+    // entry's own event; the other stream's handle is never touched again)
+    DLB_CUDA_CHECK(cudaStreamWaitEvent(stream, cache.uploaded, 0));
     cache.stream = stream;
   }
   const HostAxis &hx = cache.hx, &hy = cache.hy;
@@ -929,11 +974,11 @@ int check_slab(const StencilParams& P, int64_t ydim) {
 
 
 void dlb_axes_cache_note_layout(const void* d_workspace, int64_t xdim, int64_t ydim) {
-  AxesCache& c = axes_cache();
-  std::lock_guard<std::mutex> lock(c.mu);
-  if (c.valid && c.ws == d_workspace &&
-      ((int64_t)c.x.size() != xdim || (int64_t)c.y.size() < ydim))
-    c.valid = false;
+  AxesCache& all = axes_cache();
+  std::lock_guard<std::mutex> lock(all.mu);
+  AxesEntry* c = all.find(d_workspace);
+  if (c && c->valid && ((int64_t)c->x.size() != xdim || (int64_t)c->y.size() < ydim))
+    c->valid = false;
 }
 
 extern "C" int dlb_ftle_stencil(const double* d_flow_map, int64_t nloc, int64_t grow0,

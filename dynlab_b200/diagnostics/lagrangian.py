@@ -10,10 +10,10 @@ import numpy as np
 import torch
 
 from .. import _native as nat
-from .. import sharding
+from .. import peer, sharding
 from .._engine import Engine
 from ..utils import odeint_wrapper
-from ._base_classes import LagrangianDiagnostic2D, RidgeExtractor2D
+from ._base_classes import LagrangianDiagnostic2D, RidgeExtractor2D, _Deferred
 
 
 def _ftle_on_device(diag, local, slab, t, edge_order, xi_mode):
@@ -67,6 +67,31 @@ def pipeline_schedule(lo, hi, own0, own1, ydim, edge_order, chunks, last_fractio
     return steps
 
 
+def member_schedule(slab, ydim, edge_order, exchange, chunks, last_fraction):
+    """Chunk plan of one group member: ``(steps, tail)``.  ``steps`` as in
+    ``pipeline_schedule``; ``tail`` lists the output row ranges that have to wait for the halo
+    exchange (``exchange`` mode: K1 covers the own rows only, the rows next to a neighbour are
+    produced after ``dlb_halo_exchange``).  Without exchange the halo rows are integrated
+    locally and ``tail`` is empty."""
+    s = slab
+    if not s.rows:
+        return [], []
+    if exchange and (s.halo_lo or s.halo_hi):
+        own0, own1 = s.row0 + s.halo_lo, s.row0 + s.rows - s.halo_hi
+        if edge_order == 2 and own1 == ydim and ydim - 3 < s.row0:
+            own1 = max(own0, ydim - 1)  # the one-sided formula of the last row reads the halo row
+        if own1 > own0:
+            steps = pipeline_schedule(s.row0, s.row0 + s.rows, own0, own1, ydim, edge_order,
+                                      chunks, last_fraction)
+        else:
+            steps = [(s.row0, s.row0 + s.rows, own0, own0)]
+        done = steps[-1][3]
+        tail = [r for r in ((s.row0, own0), (done, s.row0 + s.rows)) if r[1] > r[0]]
+        return steps, tail
+    return pipeline_schedule(s.lo, s.hi, s.row0, s.row0 + s.rows, ydim, edge_order, chunks,
+                             last_fraction), []
+
+
 class FTLE(LagrangianDiagnostic2D):
     """Finite-time Lyapunov exponent field of a 2-D flow (R:lagrangian.py:9-78)."""
 
@@ -77,22 +102,25 @@ class FTLE(LagrangianDiagnostic2D):
         """Returns ``np.ma.MaskedArray[ydim, xdim]``; sets ``x, y, xdim, ydim, flow_map,
         field`` like the reference.  ``kwargs`` (rtol, atol, max_step, first_step) go to the
         integrator."""
+        group = self._group(np.size(x) * np.size(y))
+        if group is not None:  # several GPUs: row slabs, peer-memory data path (csrc/peer.cu)
+            return self._compute_group(group, self._plan(x, y, f, t, kwargs), t, edge_order, "host")
         if (sharding.world()[1] == 1 and self.pipeline_chunks > 1
                 and np.size(y) >= 64 * self.pipeline_chunks and np.size(x) * np.size(y) >= (1 << 22)):
             return self._compute_pipelined(self._plan(x, y, f, t, kwargs), t, edge_order)
-        if sharding.host_result_shared():
-            return self._compute_shared(x, y, f, t, edge_order, kwargs)
+        # one device, or sharding.set_transport("nccl"): kernels, then NCCL halo + all-gathers,
+        # then one device-to-host copy of the gathered field per rank
         field = self._run(x, y, f, t, edge_order, self.gather_flow_map, kwargs)
-        if sharding.host_result_wanted():
-            # several ranks copying at once: the staged path's worker threads and page faults
-            # contend for the host cores, one DMA into a pinned buffer per rank does not
-            many = sharding.world()[1] > 1
-            self.field = np.ma.MaskedArray(Engine.get().to_host(field, pinned=True if many else None))
-        else:  # sharding.set_host_result("rank0") on a non-zero rank: placeholder, all masked
-            torch.cuda.current_stream(field.device).synchronize()
-            self.field = np.ma.MaskedArray(np.broadcast_to(np.nan, tuple(field.shape)), mask=True)
+        many = sharding.world()[1] > 1
+        self.field = np.ma.MaskedArray(Engine.get().to_host(field, pinned=True if many else None))
         self._collect_stats()
         return self.field
+
+    @staticmethod
+    def _group(n_seeds):
+        if sharding.world()[1] > 1 and sharding.transport() != "peer":
+            return None
+        return peer.current_group(n_seeds)
 
     # Large grids: K1 runs in row chunks; as soon as a chunk's successor row exists K2 produces
     # that chunk's FTLE rows and a copy stream moves them to pinned host memory while the next
@@ -145,39 +173,195 @@ class FTLE(LagrangianDiagnostic2D):
         self._collect_stats()
         return self.field
 
-    def _compute_shared(self, x, y, f, t, edge_order, kwargs):
-        """Multi-GPU with ``sharding.set_host_result("shared")``: this rank's slab goes through
-        the same chunk pipeline straight into the host segment all ranks of the box map - no
-        device all-gather, the field crosses PCIe once in total, and the copies (bounded by the
-        box's aggregate device-to-host bandwidth, ~100 GB/s for 8 GPUs) hide behind K1.  The
-        one or two halo rows are integrated locally (bit-identical to the neighbours' rows), so
-        chunks do not wait for other ranks.  ``flow_map`` / ``field_device`` hold this rank's
-        rows only."""
-        plan = self._plan(x, y, f, t, kwargs)
-        rank, size = sharding.world()
-        slab = sharding.partition(self.ydim, size, rank)
-        host_np, host_t = sharding.shared_host_array((self.ydim, self.xdim))
-        own = None
-        self._counters_pending, self._counter_tensors = False, None
-        if slab.rows:
-            fm, own = self._pipeline(plan, t, edge_order, slab.lo, slab.hi, slab.row0,
-                                     slab.row0 + slab.rows, host_t)
-            self.flow_map = fm[slab.halo_lo:slab.halo_lo + slab.rows]
+    # ---------------------------------------------------------------------------------------
+    # Several GPUs (one process driving all of them, or one torchrun rank per GPU): every
+    # member integrates its row slab in chunks; finished FTLE rows leave the device on the copy
+    # stream while the next chunk integrates — into pinned host memory ("host": what compute()
+    # returns) or, pushed by a copy engine over NVLink, into every member's copy of the field
+    # ("device": what compute_device() returns).  Nothing is gathered afterwards and no
+    # collective library is on the data path; `flow_map` is collected from the members' buffers
+    # only if it is read.  Results are bit-identical to the single-device ones: seeds are
+    # independent and a row's stencil reads its neighbour rows only.
+    def _compute_group(self, G, plan, t, edge_order, target):
+        if edge_order > 2:
+            raise ValueError("'edge_order' greater than 2 not supported")
+        t_span = abs(float(t[-1]) - float(t[0]))
+        if t_span == 0.0:
+            raise ZeroDivisionError("float division by zero")  # R:lagrangian.py:71
+        ydim, xdim = self.ydim, self.xdim
+        G.check_timeouts()
+        bounds = self._slab_bounds(G, plan)
+        slabs = [sharding.slab_from_bounds(bounds, ydim, r) for r in range(G.size)]
+        exchange = sharding.halo_mode() == "exchange"
+        gen = G.next_generation()
+        row_b = xdim * 16
+        fm_sym = G.symmetric(("flow_map", gen % 2), max(max(s.nloc for s in slabs), 1) * row_b)
+        field_sym = host_np = host_t = None
+        if target == "device":
+            field_sym = G.symmetric(("field", gen % peer.RESULT_DEPTH), ydim * xdim * 8)
+        elif G.multiprocess:
+            host_np, host_t = sharding.shared_host_array(
+                (ydim, xdim), tag=("result", gen % peer.RESULT_DEPTH))
         else:
-            if edge_order > 2:
-                raise ValueError("'edge_order' greater than 2 not supported")
-            if float(t[-1]) == float(t[0]):
-                raise ZeroDivisionError("float division by zero")  # R:lagrangian.py:71
-        sharding.host_barrier()  # every rank's rows are in the segment
-        self.field_device = own
+            host_t = torch.empty((ydim, xdim), dtype=torch.float64, pin_memory=True)
+            host_np = host_t.numpy()
+
+        # one process per GPU: every rank ends up with the whole field; one process driving all
+        # of them: only the member whose tensor is returned needs it
+        dests = None if G.multiprocess else [G.local[0].rank]
+        runs = []
+        for m in G.local:
+            s = slabs[m.rank]
+            eng = m.engine
+            with torch.cuda.device(m.device):
+                main = torch.cuda.current_stream(m.device)
+                main.wait_stream(eng.copy_stream)  # pushes of earlier calls out of reused buffers
+                steps, tail = member_schedule(s, ydim, edge_order, exchange, self.pipeline_chunks,
+                                              self.pipeline_last_fraction)
+                fm = fm_sym.view(m, torch.float64, (max(s.nloc, 1), xdim, 2))
+                if target == "device":
+                    out = field_sym.view(m, torch.float64, (ydim, xdim))  # global row index
+                    out_row0 = 0
+                else:
+                    out = eng.empty(max(s.rows, 1), xdim)
+                    out_row0 = s.row0
+                counters = torch.zeros(max(len(steps), 1), nat.CNT_WORDS, dtype=torch.int64,
+                                       device=m.device)
+            runs.append(dict(m=m, s=s, steps=steps, tail=tail, fm=fm, out=out, out_row0=out_row0,
+                             counters=counters, main=main, pushes=0))
+
+        def ship(run, a, b, last):
+            """FTLE rows [a, b) of this member were just enqueued on its main stream: send
+            them on their way on the copy stream."""
+            m, eng = run["m"], run["m"].engine
+            with torch.cuda.device(m.device):
+                ev = torch.cuda.Event()
+                ev.record(run["main"])
+                eng.copy_stream.wait_event(ev)
+                if target == "device":
+                    run["pushes"] += 1
+                    value = gen * peer.GEN_STRIDE + (peer.DONE if last else min(run["pushes"], peer.DONE - 1))
+                    G.push_rows(m, field_sym, a * xdim * 8, (b - a) * xdim * 8, value,
+                                eng.copy_stream.cuda_stream, dests)
+                elif b > a:
+                    with torch.cuda.stream(eng.copy_stream):
+                        r0 = run["out_row0"]
+                        host_t[a:b].copy_(run["out"][a - r0:b - r0], non_blocking=True)
+
+        def stencil(run, g0, g1, a, b):
+            """K2: FTLE rows [a, b) from the member's flow-map rows [g0, g1) (global indices)."""
+            eng, r0, lo = run["m"].engine, run["out_row0"], run["s"].lo
+            with torch.cuda.device(run["m"].device):
+                eng.ftle_stencil(run["fm"][g0 - lo:g1 - lo], g0, self._xf, self._yf, edge_order,
+                                 t_span, a, b - a, out=run["out"][a - r0:b - r0])
+
+        # chunk-major over the local members, so that every device has work queued before the
+        # host moves on to the next chunk
+        for c in range(max([len(r["steps"]) for r in runs] + [0])):
+            for run in runs:
+                if c >= len(run["steps"]):
+                    continue
+                m, s = run["m"], run["s"]
+                r0, r1, done, upto = run["steps"][c]
+                lo = s.lo  # fm row 0 is global row s.lo (halo slot included)
+                with torch.cuda.device(m.device):
+                    self._integrate_rows(plan, r0, r1 - r0, run["fm"][r0 - lo:r1 - lo],
+                                         counters=run["counters"][c], eng=m.engine)
+                if upto > done:
+                    stencil(run, run["steps"][0][0], r1, done, upto)
+                    last = c == len(run["steps"]) - 1 and not run["tail"]
+                    ship(run, done, upto, last)
+        # 1-row halo exchange (dlb_halo_exchange: every member pushes first, then waits), then the
+        # rows that were waiting for it
+        for run in runs:
+            if run["tail"]:
+                G.halo_push(run["m"], fm_sym, row_b, slabs, gen, run["main"].cuda_stream)
+        for run in runs:
+            m, s = run["m"], run["s"]
+            if run["tail"]:
+                G.halo_wait(m, slabs, gen, run["main"].cuda_stream)
+                for k, (a, b) in enumerate(run["tail"]):
+                    stencil(run, s.lo, s.hi, a, b)
+                    ship(run, a, b, k == len(run["tail"]) - 1)
+            elif not s.rows:
+                ship(run, 0, 0, True)  # nothing to send: still tell the others we are done
+
+        self._counters_pending = True
+        self._counter_tensors = [r["counters"] for r in runs if r["s"].rows]
+        first = runs[0]
+        cache = {}
+        self.flow_map = _Deferred(lambda: self._gather_flow_map(G, fm_sym, slabs, first["m"]), 0,
+                                  cache)
+        if target == "device":
+            for run in runs:
+                if dests is None or run["m"].rank in dests:
+                    G.wait_gathered(run["m"], gen, run["main"].cuda_stream)
+            self.field_device = first["out"]
+            return first["out"]
+        for run in runs:
+            run["m"].engine.copy_stream.synchronize()
+            if run["s"].rows:
+                run["out"].record_stream(run["m"].engine.copy_stream)
+        G.check_timeouts()
+        if G.multiprocess:
+            sharding.host_barrier()  # every rank's rows are in the segment
+            if sharding.host_result_mode() == "private":
+                host_np = host_np.copy()
+        self.field_device = first["out"]
         self.field = np.ma.MaskedArray(host_np)
         self._collect_stats()
         return self.field
 
+    def _slab_bounds(self, G, plan):
+        """Row boundaries of the members' slabs: equal work (pilot run, `_row_costs`) when the
+        grid is large enough to care, equal rows otherwise.  With one process per GPU rank 0's
+        estimate is broadcast once per (flow, t, grid) so that all ranks cut at the same rows."""
+        key = ("bounds", G.size, plan["fid"], tuple(plan["params"]), plan["t0"], plan["tf"],
+               plan["rtol"], plan["atol"], self._xf.tobytes(), self._yf.tobytes())
+        b = self._row_cost_cache.get(key)
+        if b is None:
+            b = sharding.uniform_bounds(self.ydim, G.size)
+            if self.weighted_slabs and G.size > 1:
+                if G.multiprocess:
+                    import torch.distributed as dist
+
+                    box = [None]
+                    if G.local[0].rank == 0:
+                        cost = self._row_costs(plan, G.local[0].engine)
+                        box[0] = None if cost is None else sharding.weighted_bounds(self.ydim, G.size, cost)
+                    dist.broadcast_object_list(box, src=0)
+                    b = box[0] or b
+                else:
+                    cost = self._row_costs(plan, G.local[0].engine)
+                    if cost is not None:
+                        b = sharding.weighted_bounds(self.ydim, G.size, cost)
+            self._row_cost_cache[key] = b
+        return b
+
+    weighted_slabs = True  # cut the slabs by integrator work instead of by rows (large grids)
+
+    def _gather_flow_map(self, G, fm_sym, slabs, m):
+        """The reference's `flow_map` attribute (R:_base_classes.py:187): collected on demand by
+        one-sided reads of the members' buffers (`dlb_peer_copy`), valid until the next-but-one
+        compute of this group."""
+        ydim, xdim = self.ydim, self.xdim
+        with torch.cuda.device(m.device):
+            full = m.engine.empty(ydim, xdim, 2)
+            stream = torch.cuda.current_stream(m.device).cuda_stream
+            for r, s in enumerate(slabs):
+                if s.rows:
+                    G.pull(m, full[s.row0:s.row0 + s.rows], fm_sym, r, s.halo_lo * xdim * 16, stream)
+        return (full,)
+
     def compute_device(self, x, y, f, t, edge_order: int = 1, **kwargs):
         """Same computation, result left on the device (``torch.Tensor[ydim, xdim]``, also kept
-        as ``field_device``); nothing is synchronised or copied to the host.  Under multi-GPU
-        sharding the flow map is not gathered: ``flow_map`` holds this rank's rows only."""
+        as ``field_device``); nothing is synchronised or copied to the host.  On several GPUs
+        every member ends up with the whole field (the tensor returned is the first local
+        member's); it lives in one of ``peer.RESULT_DEPTH`` rotating buffers, i.e. it keeps its
+        values through the next call and is overwritten by the one after."""
+        group = self._group(np.size(x) * np.size(y))
+        if group is not None:
+            return self._compute_group(group, self._plan(x, y, f, t, kwargs), t, edge_order, "device")
         return self._run(x, y, f, t, edge_order, False, kwargs)
 
     def _run(self, x, y, f, t, edge_order, gather_flow_map, kwargs):
@@ -196,6 +380,7 @@ class LCS(LagrangianDiagnostic2D, RidgeExtractor2D):
 
     def __init__(self, integrator=odeint_wrapper, num_threads: int = 1) -> None:
         super().__init__(integrator=integrator, num_threads=num_threads)
+        self.gather_flow_map = False  # deleted right after the stencil (R:lagrangian.py:137-139)
 
     def compute(self, x, y, f, t, edge_order: int = 1, percentile: float = None,
                 force_eigenvectors: bool = False, debug: bool = False, **kwargs):

@@ -58,6 +58,8 @@ def host_barrier(timeout_s: float = 120.0) -> None:
     spins = 0
     while int(flags[:size].min()) < gen:
         spins += 1
+        if spins > 200:  # the others are more than a few us away: stop burning the core
+            os.sched_yield() if spins < 20000 else time.sleep(50e-6)
         if spins & 0x3ff == 0 and time.monotonic() > deadline:
             raise RuntimeError("host_barrier: a rank did not arrive (died or never called it)")
 
@@ -77,32 +79,56 @@ def halo_mode() -> str:
     return _halo
 
 
-_host_result = "all"  # which ranks receive the gathered field in host memory
+_host_result = "shared"  # how the ranks of a torchrun job receive the field in host memory
 
 
 def set_host_result(which) -> None:
-    """``"all"`` (default): every rank's ``compute`` returns its own copy of the full field on
-    the host, like the single-process reference.  ``"rank0"``: only rank 0 copies it to the host
-    (the other ranks get a fully masked placeholder of the same shape) — at 8 GPUs the eight
-    simultaneous 268 MB device-to-host copies of config 3 cost more than the whole computation.
-    ``"shared"``: the ranks of the box share one pinned host segment (``shared_host_array``);
-    each rank copies only its own rows into it and every rank returns a view of the whole, so the
-    field crosses PCIe once instead of once per rank and no device all-gather is needed.  The
-    price is aliasing: the returned array is the same memory on every rank and the next
-    ``compute`` on a grid of the same size overwrites it — copy it if it must outlive that."""
+    """One process per GPU: how every rank's ``FTLE.compute`` gets the full host field.
+    ``"shared"`` (default): the ranks of the box share pinned host segments
+    (``shared_host_array``); each rank streams only its own rows into the segment while it is
+    still integrating and every rank returns a view of the whole, so the field crosses PCIe once
+    instead of once per rank and nothing is gathered on the devices.  The segments rotate
+    (``peer.RESULT_DEPTH`` = 3 per grid shape): a returned array keeps its values through the
+    next ``compute`` of that shape and is overwritten by the one after; it is the same memory on
+    every rank.  ``"private"``: each rank returns its own ordinary numpy copy (costs a
+    ydim*xdim*8-byte host memcpy per rank per call)."""
     global _host_result
-    if which not in ("all", "rank0", "shared"):
-        raise ValueError('which must be "all", "rank0" or "shared"')
+    if which == "all":  # round-1 name of the private-copy mode
+        which = "private"
+    if which not in ("shared", "private"):
+        raise ValueError('which must be "shared" or "private"')
     _host_result = which
 
 
-def host_result_wanted() -> bool:
-    rank, size = world()
-    return _host_result in ("all", "shared") or size == 1 or rank == 0
+def host_result_mode() -> str:
+    return _host_result
 
 
-def host_result_shared() -> bool:
-    return _host_result == "shared" and world()[1] > 1
+_transport = "peer"
+
+
+def set_transport(which) -> None:
+    """One process per GPU: what carries the halo rows and the gathered field between the
+    devices.  ``"peer"`` (default): this library's own peer-memory path (``csrc/peer.cu``: copy
+    engine writes into CUDA-IPC mapped buffers + generation flags, overlapped with the
+    integrator chunk by chunk).  ``"nccl"``: torch.distributed point-to-point + all-gather after
+    the kernels (the round-1 path, kept for A/B measurements and as the path of LCS and the
+    Eulerian diagnostics)."""
+    global _transport
+    if which not in ("peer", "nccl"):
+        raise ValueError('which must be "peer" or "nccl"')
+    _transport = which
+
+
+def transport() -> str:
+    return _transport
+
+
+def set_devices(spec) -> None:
+    """Single process: devices a Lagrangian ``compute`` is sharded over (see ``peer.set_devices``)."""
+    from . import peer
+
+    peer.set_devices(spec)
 
 
 _segments = {}  # (tag, nbytes) -> (mmap object, flat uint8 ndarray)
@@ -139,7 +165,7 @@ def shared_host_array(shape, dtype=np.float64, tag="result"):
         dist.barrier()
         if rank == 0:
             os.unlink(name[0])
-        if torch.cuda.is_available() and dist.get_backend() == "nccl":
+        if torch.cuda.is_available():
             torch.cuda.check_error(
                 torch.cuda.cudart().cudaHostRegister(flat.ctypes.data, max(nbytes, 1), 0))
         seg = _segments[key] = (mm, flat)
@@ -194,6 +220,44 @@ def partition(ydim: int, size: int, rank: int) -> Slab:
     lo = row0 - 1 if rank > 0 else row0
     hi = row0 + rows + (1 if rank < n - 1 else 0)
     return Slab(row0, rows, lo, hi, rows_max)
+
+
+def uniform_bounds(ydim: int, size: int) -> list:
+    """Row boundaries ``b[0..size]`` of ``partition``: rank r owns rows [b[r], b[r+1])."""
+    out = [partition(ydim, size, r).row0 for r in range(size)] + [ydim]
+    return [min(b, ydim) for b in out]
+
+
+def weighted_bounds(ydim: int, size: int, row_cost) -> list:
+    """Boundaries that give every active rank the same share of ``sum(row_cost)`` (a per-row
+    work estimate, e.g. integrator attempts), every slab keeping >= 2 rows.  Deterministic in
+    its inputs, so ranks that hold the same estimate agree without talking."""
+    n = active_ranks(ydim, size)
+    cost = np.maximum(np.asarray(row_cost, dtype=np.float64), 0.0)
+    if n == 1 or cost.shape != (ydim,) or not np.isfinite(cost).all() or cost.sum() <= 0:
+        return uniform_bounds(ydim, size)
+    cum = np.concatenate(([0.0], np.cumsum(cost)))
+    b = [0]
+    for k in range(1, n):
+        target = cum[-1] * k / n
+        i = int(np.searchsorted(cum, target, side="left"))
+        if i > 0 and target - cum[i - 1] < cum[i] - target:
+            i -= 1  # the boundary nearer to the target
+        i = max(i, b[-1] + 2)            # >= 2 rows for slab k-1 ...
+        i = min(i, ydim - 2 * (n - k))   # ... and for every slab still to come
+        b.append(i)
+    return b + [ydim] * (size - n + 1)
+
+
+def slab_from_bounds(bounds, ydim: int, rank: int) -> Slab:
+    """``Slab`` of ``rank`` for arbitrary boundaries (1-row halo towards existing neighbours)."""
+    row0, row1 = bounds[rank], bounds[rank + 1]
+    rows = row1 - row0
+    rows_max = max(b1 - b0 for b0, b1 in zip(bounds[:-1], bounds[1:]))
+    if rows == 0:
+        return Slab(ydim, 0, ydim, ydim, rows_max)
+    return Slab(row0, rows, row0 - 1 if row0 > 0 else row0, row1 + 1 if row1 < ydim else row1,
+                rows_max)
 
 
 def exchange_halo(local: torch.Tensor, slab: Slab, ydim: int, rank: int, size: int) -> None:

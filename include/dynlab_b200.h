@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DLB_ABI_VERSION 1
+#define DLB_ABI_VERSION 2
 
 enum dlb_error {
   DLB_OK = 0,
@@ -229,6 +229,53 @@ size_t dlb_select_scratch_bytes(void);
 int dlb_order_statistics(const double* d_values, int64_t n, const int64_t* h_ranks, int nranks,
                          double* d_out, uint64_t* d_nan_count, void* d_scratch,
                          size_t scratch_bytes, void* stream);
+
+/* ---- multi-GPU helpers (SURVEY §8b "multi-GPU helpers", §8e) -------------------------------
+ * The reference's only parallel construct is a process pool whose per-seed results `p.map`
+ * collects into one array (R:src/dynlab/diagnostics/_base_classes.py:139-148, :178-187).  Here
+ * the seed grid is split into row slabs over the GPUs of one box; these entry points are the
+ * collection step and the stencil's 1-row halo, done by the GPUs themselves over NVLink peer
+ * memory: a copy engine writes the rows into the receivers' buffers while the SMs go on
+ * integrating, then one warp releases a generation flag in each receiver's memory
+ * (st.release.sys); the receiver's stream waits on its own flags with dlb_wait_flags.
+ * "Symmetric" buffers are plain device allocations every participating GPU can address:
+ * inside one process after dlb_peer_enable, between the one-process-per-GPU ranks through the
+ * 64-byte handle of dlb_ipc_export opened with dlb_ipc_open (CUDA IPC; the handle bytes travel
+ * by whatever channel the host has - dynlab_b200 uses torch.distributed object collectives). */
+#define DLB_MAX_PEERS 16
+#define DLB_IPC_HANDLE_BYTES 64
+int dlb_device_count(int* n);
+/* Let `device` address `peer`'s memory (idempotent).  Single-process multi-device use. */
+int dlb_peer_enable(int device, int peer);
+/* Zero-filled allocation on the current device that can be exported with dlb_ipc_export. */
+int dlb_peer_alloc(size_t bytes, void** d_ptr);
+int dlb_peer_free(void* d_ptr);
+int dlb_ipc_export(const void* d_ptr, unsigned char handle[DLB_IPC_HANDLE_BYTES]);
+/* Map another process's dlb_peer_alloc block into this process (peer access enabled lazily). */
+int dlb_ipc_open(const unsigned char handle[DLB_IPC_HANDLE_BYTES], void** d_ptr);
+int dlb_ipc_close(void* d_ptr);
+/* Stream-ordered copy between any two addresses this process can address (own device, peer
+ * device, IPC-mapped peer, pinned host): the one-sided read used to collect `flow_map` rows. */
+int dlb_peer_copy(void* d_dst, const void* d_src, size_t bytes, void* stream);
+/* Row gather, push side: copy [d_src, d_src + bytes) to each d_dst[i] (i < n_dst <=
+ * DLB_MAX_PEERS; NULL or == d_src entries are skipped), then publish `flag_value` at every
+ * non-NULL d_flags[i] with release semantics at system scope.  Flags are uint64 generation
+ * counters in the receivers' memory and must only grow. */
+int dlb_gather_rows(const void* d_src, size_t bytes, void* const* d_dst, int n_dst,
+                    uint64_t* const* d_flags, uint64_t flag_value, void* stream);
+/* 1-row halo exchange, push side: row `first_own` of d_local ([nloc][row_bytes]) goes to the
+ * upper neighbour's bottom halo slot d_up_slot, row `last_own` to the lower neighbour's top halo
+ * slot d_down_slot (NULL = no such neighbour), then `flag_value` is released at d_up_flag /
+ * d_down_flag (in the neighbours' memory). */
+int dlb_halo_exchange(const void* d_local, size_t row_bytes, int64_t first_own, int64_t last_own,
+                      void* d_up_slot, void* d_down_slot, uint64_t* d_up_flag,
+                      uint64_t* d_down_flag, uint64_t flag_value, void* stream);
+/* Receive side of both: enqueue a one-warp kernel that polls d_flags[0..n) (n <= 32, this
+ * device's memory) until every one is >= min_value (acquire at system scope), so later work
+ * on `stream` sees the rows.  Bounded: after timeout_s seconds it gives up and stores
+ * 1 + (index of a late flag) to *d_timed_out (int, may be NULL) instead of hanging the GPU. */
+int dlb_wait_flags(const uint64_t* d_flags, int n, uint64_t min_value, double timeout_s,
+                   int* d_timed_out, void* stream);
 
 /* FP64 roofline denominator: runs a register-resident DFMA chain kernel and returns the
  * sustained FP64 throughput in FLOP/s (FMA = 2) through *flops_per_s.  Synchronises. */

@@ -967,18 +967,74 @@ def test_eulerian_c2_full_size_properties(dl):
     assert np.abs(tr).max() < 1e-3 * np.abs(rep).max()
 
 
-def test_multi_gpu_sharding_matches_single(dl):
-    """N >= 2 GPUs: row-sharded results (NCCL halo exchange + all-gather) are bit-identical to
-    the single-GPU ones.  Skipped on a 1-GPU box (the gloo tests cover the host logic there)."""
+def _torchrun_check(n, extra, port):
     import os
     import subprocess
     import sys
 
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(root, "tools", "check_multigpu.py")] + extra
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    assert "MULTIGPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    return out.stdout
+
+
+def test_multi_gpu_sharding_matches_single(dl):
+    """N >= 2 GPUs, one process per GPU: row-sharded results — peer-memory transport
+    (dlb_gather_rows / dlb_halo_exchange over CUDA IPC) and NCCL transport, both halo modes,
+    shared / private host result, device result, work- and row-cut slabs — are bit-identical to
+    the single-GPU ones.  Skipped on a 1-GPU box (next test covers the data path there)."""
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}",
-           "--master-addr", "127.0.0.1", "--master-port", "29617", os.path.join(root, "tools", "check_multigpu.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
-    assert "MULTIGPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    _torchrun_check(min(n, 4), [], 29617)
+
+
+def test_multi_process_peer_path_on_one_gpu(dl):
+    """The same one-process-per-GPU data path with every rank on cuda:0 (CUDA IPC between three
+    processes sharing the GPU, gloo for the plumbing): symmetric buffers, generation flags,
+    push gather, halo exchange and the shared host segment, bit-identical to the single run."""
+    _torchrun_check(3, ["--backend", "gloo", "--same-device"], 29631)
+
+
+def test_single_process_group_matches_single_device(dl):
+    """One plain process driving a group of GPUs (the reference creates and tears
+    down its parallelism inside one blocking call, R:_base_classes.py:139-148).  With one GPU
+    the group is three members on cuda:0, with more it is every visible device; either way
+    compute(), compute_device() and flow_map equal the single-device results bit for bit."""
+    from dynlab_b200 import peer, sharding
+
+    D, fl = dl.diagnostics, dl.flows
+    n = torch.cuda.device_count()
+    spec = list(range(n)) if n > 1 else [0, 0, 0]
+    try:
+        for (nx, ny, eo, t) in ((257, 131, 2, (6, 0)), (64, 5, 1, (6, 0)), (33, 3, 2, (6, 0)),
+                                (2048, 1030, 2, (3, 0))):
+            x, y = np.linspace(0, 2, nx), np.linspace(0, 1, ny)
+            kw = dict(edge_order=eo, rtol=1e-8, atol=1e-8)
+            peer.set_devices(None)
+            d1 = D.FTLE()
+            f1 = np.ma.getdata(d1.compute(x, y, fl.double_gyre, t, **kw)).copy()
+            fm1 = d1.flow_map.copy()
+            peer.set_devices(spec)
+            for halo in ("exchange", "redundant"):
+                sharding.set_halo_mode(halo)
+                for weighted in (True, False):
+                    d = D.FTLE()
+                    d.weighted_slabs = weighted
+                    f = np.ma.getdata(d.compute(x, y, fl.double_gyre, t, **kw))
+                    assert np.array_equal(f, f1), (nx, ny, halo, weighted)
+                    if halo == "exchange":
+                        assert d.stats["nfev"] == d1.stats["nfev"]
+                    assert np.array_equal(d.flow_map, fm1), (nx, ny, halo, weighted)
+                    for rep in range(4):  # rotating result buffers
+                        fd = d.compute_device(x, y, fl.double_gyre, t, **kw)
+                        assert np.array_equal(fd.cpu().numpy(), f1), (nx, ny, halo, weighted, rep)
+            peer.current_group(nx * ny).check_timeouts()
+    finally:
+        peer.set_devices("auto")
+        sharding.set_halo_mode("exchange")
+
+

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/dynlab_b200.h but not exported"
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
-    assert _native.lib.dlb_abi_version() == 1
+    assert _native.lib.dlb_abi_version() == 2
 
 
 def test_flow_registry_matches_abi():
@@ -253,8 +253,7 @@ def _shared_worker(rank, size, port, out_dir):
     try:
         from dynlab_b200 import sharding
 
-        sharding.set_host_result("shared")
-        assert sharding.host_result_shared() and sharding.host_result_wanted()
+        assert sharding.host_result_mode() == "shared"  # the default
         ydim, xdim = 11, 7
         for rep in range(2):
             arr, ten = sharding.shared_host_array((ydim, xdim))
@@ -282,10 +281,17 @@ def _shared_worker(rank, size, port, out_dir):
         n_before = len(sharding._segments)
         other, _ = sharding.shared_host_array((3, 5))
         assert other.shape == (3, 5) and len(sharding._segments) == n_before + 1
-        sharding.set_host_result("all")
-        assert not sharding.host_result_shared()
+        sharding.set_host_result("private")
+        assert sharding.host_result_mode() == "private"
+        sharding.set_host_result("shared")
         with pytest.raises(ValueError):
             sharding.set_host_result("everyone")
+        # rotating result segments are distinct mappings
+        a0, _ = sharding.shared_host_array((4, 4), tag=("result", 0))
+        a1, _ = sharding.shared_host_array((4, 4), tag=("result", 1))
+        a0[:] = 1.0
+        a1[:] = 2.0
+        assert (a0 == 1.0).all() and (a1 == 2.0).all()
         if rank == 0:
             open(os.path.join(out_dir, "ok_shared"), "w").write("ok")
     finally:
@@ -310,7 +316,48 @@ def test_sharding_mode_switches_validate():
         sharding.set_halo_mode("both")
     with pytest.raises(ValueError):
         sharding.set_host_result("nobody")
-    assert sharding.host_result_wanted() and not sharding.host_result_shared()  # no process group
+    assert sharding.host_result_mode() == "shared"
+    sharding.set_host_result("all")  # round-1 name of the private-copy mode
+    assert sharding.host_result_mode() == "private"
+    sharding.set_host_result("shared")
+    assert sharding.transport() == "peer"
+    sharding.set_transport("nccl")
+    assert sharding.transport() == "nccl"
+    sharding.set_transport("peer")
+    with pytest.raises(ValueError):
+        sharding.set_transport("mpi")
+
+
+def test_weighted_bounds():
+    """Cost-weighted slabs: cover the grid, keep >= 2 rows per active rank, equalise the cost,
+    reduce to the uniform partition for a flat cost, and agree with `partition` through
+    `slab_from_bounds`."""
+    from dynlab_b200 import sharding as sh
+
+    rng = np.random.default_rng(5)
+    for ydim in (2, 3, 5, 16, 101, 4096):
+        for size in (1, 2, 3, 8):
+            ub = sh.uniform_bounds(ydim, size)
+            assert [sh.slab_from_bounds(ub, ydim, r) for r in range(size)] == \
+                   [sh.partition(ydim, size, r) for r in range(size)]
+            n = sh.active_ranks(ydim, size)
+            for cost in (rng.uniform(0.5, 2.0, ydim), np.linspace(1, 30, ydim),
+                         np.r_[np.zeros(ydim // 2), np.ones(ydim - ydim // 2)]):
+                wb = sh.weighted_bounds(ydim, size, cost)
+                assert len(wb) == size + 1 and wb[0] == 0 and wb[-1] == ydim
+                assert all(b1 - b0 >= min(2, ydim) for b0, b1 in zip(wb[:n], wb[1:n + 1]))
+                assert all(b == ydim for b in wb[n:])
+                slabs = [sh.slab_from_bounds(wb, ydim, r) for r in range(size)]
+                assert sum(s.rows for s in slabs) == ydim
+                for r, s in enumerate(slabs[:n]):
+                    assert s.lo == max(s.row0 - 1, 0) and s.hi == min(s.row0 + s.rows + 1, ydim)
+            assert sh.weighted_bounds(ydim, size, np.ones(ydim)) == ub or ydim % max(n, 1)
+    cost = np.linspace(1, 30, 4096)
+    wb = sh.weighted_bounds(4096, 8, cost)
+    shares = [cost[a:b].sum() for a, b in zip(wb[:-1], wb[1:])]
+    assert max(shares) / np.mean(shares) < 1.01
+    assert sh.weighted_bounds(4096, 8, np.full(4096, np.nan)) == sh.uniform_bounds(4096, 8)
+    assert sh.weighted_bounds(4096, 8, np.ones(7)) == sh.uniform_bounds(4096, 8)
 
 
 def test_deferred_attribute_resolves_once():
@@ -378,6 +425,53 @@ def test_pipeline_schedule_invariants():
                         s = partition(ydim, size, rank)
                         if s.rows:
                             check(s.lo, s.hi, s.row0, s.row0 + s.rows, ydim, eo, chunks, frac)
+
+
+def test_member_schedule_invariants():
+    """Group path (several GPUs): for uniform and weighted partitions, both halo modes, every own
+    output row is produced exactly once, in order, and only from rows that exist locally at that
+    moment (integrated chunks; after the exchange also the halo slots)."""
+    from dynlab_b200 import sharding as sh
+    from dynlab_b200.diagnostics.lagrangian import member_schedule
+
+    def need(a, b, ydim, eo):
+        lo, hi = max(a - 1, 0), min(b, ydim - 1)
+        if eo == 2 and a == 0:
+            hi = max(hi, min(2, ydim - 1))
+        if eo == 2 and b == ydim:
+            lo = min(lo, max(ydim - 3, 0))
+        return lo, hi
+
+    rng = np.random.default_rng(11)
+    for ydim in (3, 4, 5, 17, 64, 257, 1000, 4096):
+        for size in (2, 3, 8):
+            for bounds in (sh.uniform_bounds(ydim, size),
+                           sh.weighted_bounds(ydim, size, rng.uniform(0.2, 3.0, ydim))):
+                for eo in (1, 2):
+                    for exchange in (False, True):
+                        for rank in range(size):
+                            s = sh.slab_from_bounds(bounds, ydim, rank)
+                            steps, tail = member_schedule(s, ydim, eo, exchange, 4, 32)
+                            if not s.rows:
+                                assert steps == [] and tail == []
+                                continue
+                            k0, k1 = (s.row0, s.row0 + s.rows) if exchange else (s.lo, s.hi)
+                            assert steps[0][0] == k0 and steps[-1][1] == k1
+                            assert all(a[1] == b[0] for a, b in zip(steps, steps[1:]))
+                            produced = []
+                            for _, r1, done, upto in steps:
+                                if upto > done:
+                                    lo, hi = need(done, upto, ydim, eo)
+                                    assert k0 <= lo and hi < r1
+                                    produced.append((done, upto))
+                            if not exchange:
+                                assert tail == []
+                            for a, b in tail:  # after the exchange the whole [s.lo, s.hi) is local
+                                lo, hi = need(a, b, ydim, eo)
+                                assert s.lo <= lo and hi < s.hi
+                                produced.append((a, b))
+                            rows = sorted(r for a, b in produced for r in range(a, b))
+                            assert rows == list(range(s.row0, s.row0 + s.rows)), (ydim, size, rank, eo, exchange)
 
 
 def test_bench_reference_arm_json_contract():
