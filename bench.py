@@ -48,6 +48,7 @@ F_RHS = 18 + 5 * 20
 F_ATTEMPT = 6 * F_RHS + 64 * 2 + 16 + 20   # 872
 F_SEED = 2 * F_RHS + 10 * 2                # 256
 BYTES_PER_POINT_K2 = 24
+TRAFFIC_FILE = "r01_traffic.json"
 
 
 def grid(stride: int = 1):
@@ -254,6 +255,147 @@ def reference_subprocess(seeds: int, integrator: str, steps: int = 1):
 
 
 # ------------------------------------------------------------------------- GPU arm
+def sha256_of(a) -> str:
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def oracle_sample_error(flow_map_sample, stride=64):
+    """max |flow_map - C oracle| on the every-`stride`-th row/column sample of config 3 (the
+    oracle leg bench.py is allowed: checker of the result, never the thing measured)."""
+    from oracle import c_oracle as co
+    from oracle import py_oracle as po
+
+    x, y = grid(stride)
+    fm, _, _ = co.flow_map("double_gyre", po.flow_params("double_gyre"), x, y, float(T_SPAN[0]),
+                           float(T_SPAN[1]), TOL, TOL, nthreads=host_cores())
+    return float(np.abs(np.asarray(flow_map_sample) - fm).max()), int(x.size * y.size)
+
+
+def extra_configs(eng, hbm_peak, world, rank, quick):
+    """Driver-timed lines for BASELINE configs[1], [3], [4] (the headline is configs[2]).  Each
+    carries an oracle check on a sample.  CUDA events for kernels, wall clock for API calls."""
+    import torch
+
+    from dynlab_b200 import _native as nat
+    from dynlab_b200 import flows, sharding
+    from dynlab_b200._resolve import resolve_flow
+    from dynlab_b200.diagnostics import FTLE, AttractionRate
+    from dynlab_b200.sweep import ftle_time_sweep
+    from oracle import c_oracle as co
+    from oracle import py_oracle as po
+
+    def ev_ms(fn, n=5, warm=2):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(n):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    out = {}
+    sharding.set_distributed(False)  # every section below runs on this rank's GPU alone
+    try:
+        if rank == 0 and not quick:
+            # ---- configs[1]: Eulerian stencil + eigen on the Bickley jet, 8192 x 8192
+            N = 8192
+            _, fid, _, params = resolve_flow(flows.bickley_jet)
+            x, y = np.linspace(0, 20000, N), np.linspace(-4000, 4000, N)
+            u, v = eng.flow_eval_grid(fid, params, 0.0, x, y)
+            c2 = {"grid": [N, N], "edge_order": 2, "hbm_peak_gbs": hbm_peak, "kernels": {}}
+            for name, mode, xi, nbytes in (("attraction_rate_s_min", nat.EULER_S_MIN, 0, 24),
+                                           ("iles_eigen_s_min_xi", nat.EULER_S_MIN, 2, 40)):
+                ms = ev_ms(lambda: eng.euler_stencil(mode, u, v, 0, x, y, 2, 0, N, False, xi))
+                gbs = nbytes * N * N / ms / 1e6
+                c2["kernels"][name] = {"ms": ms, "bytes_per_point": nbytes, "GB_per_s": gbs,
+                                       "frac_of_hbm_peak": gbs / hbm_peak}
+            ms = ev_ms(lambda: eng.euler_stencil_flow(nat.EULER_S_MIN, fid, params, 0.0, x, y, 2,
+                                                      0, N, False, 0))
+            c2["kernels"]["attraction_rate_fused_flow"] = {"ms": ms, "bytes_per_point": 8,
+                                                           "GB_per_s": 8 * N * N / ms / 1e6}
+            uh, vh = u.cpu().numpy(), v.cpu().numpy()
+            d = AttractionRate()
+            d.compute(x, y, u=uh, v=vh, edge_order=2)
+            t0 = time.perf_counter()
+            att = d.compute(x, y, u=uh, v=vh, edge_order=2)
+            c2["e2e_host_uv_ms"] = (time.perf_counter() - t0) * 1e3
+            c2["e2e_h2d_bytes"], c2["e2e_d2h_bytes"] = 2 * 8 * N * N, 8 * N * N
+            sl = (slice(4000, 4064), slice(3000, 3064))
+            ref = po.attraction_repulsion_rate(x[sl[1]], y[sl[0]], u=uh[sl], v=vh[sl], edge_order=2)
+            gs = float(np.abs(uh).max() / (x[1] - x[0]))
+            c2["oracle_check"] = {"sample": "64x64 interior patch vs oracle/py_oracle (np.gradient + "
+                                            "np.linalg.eig), 3844 interior points",
+                                  "max_abs_err_over_gradient_scale": float(
+                                      np.abs(np.ma.getdata(att)[sl][1:-1, 1:-1]
+                                             - np.ma.getdata(ref)[1:-1, 1:-1]).max() / gs)}
+            out["config2_eulerian_bickley_8192"] = c2
+            del u, v, uh, vh, att, d
+            torch.cuda.empty_cache()
+
+            # ---- configs[3]: FTLE on flows whose step counts diverge, 4096 x 4096
+            c4 = []
+            for name, x, y, t in (
+                    ("bead_on_a_rotating_hoop", np.linspace(-1, 1, 4096) * 3, np.linspace(-1, 1, 4096) * 2.5, (0.0, 2.0)),
+                    ("duffing_oscillator", np.linspace(-2, 2, 4096), np.linspace(-2, 2, 4096), (0.0, 10.0)),
+                    ("duffing_oscillator", np.linspace(-2, 2, 4096), np.linspace(-2, 2, 4096), (10.0, 0.0))):
+                f = getattr(flows, name)
+                d = FTLE()
+                kw = dict(edge_order=2, rtol=TOL, atol=TOL)
+                ms = ev_ms(lambda: d.compute_device(x, y, f, t, **kw), n=3, warm=1)
+                st = eng.read_counters()
+                attempts = (st["nfev"] - 2 * st["seeds"]) / 6.0
+                fm_s = d.flow_map[::64, ::64]
+                fm_o, _, _ = co.flow_map(name, po.flow_params(name), x[::64], y[::64], t[0], t[1],
+                                         TOL, TOL, nthreads=host_cores())
+                scale = np.maximum(np.abs(fm_o), 1.0)
+                c4.append({"flow": name, "grid": [4096, 4096], "t": list(t), "ms": ms,
+                           "seeds_per_s": 4096 * 4096 / ms * 1e3,
+                           "attempts_per_s": attempts / ms * 1e3,
+                           "mean_nfev_per_seed": st["nfev"] / st["seeds"], "failed_seeds": st["failed"],
+                           "oracle_check": {"sample": "every 64th row and column, 4096 seeds, C oracle",
+                                            "max_rel_err_flow_map": float((np.abs(fm_s - fm_o) / scale).max())}})
+                del d
+            out["config4_divergent_step_counts_4096"] = c4
+            torch.cuda.empty_cache()
+        # ---- configs[4]: 64 t0 slices of the double gyre 4096 x 2048, T = 20, LCS ridge lines
+        sharding.set_distributed(True)  # slices are dealt round-robin over the ranks, no comms
+        x, y = np.linspace(0, 2, 4096), np.linspace(0, 1, 2048)
+        spans = [(k * 10.0 / 64 + 20.0, k * 10.0 / 64) for k in range(64)]
+        kw = dict(edge_order=2, percentile=80, ridge=True, to_host=False, rtol=TOL, atol=TOL)
+        ftle_time_sweep(x, y, flows.double_gyre, spans[:world], **kw)  # warm-up: one slice per rank
+        torch.cuda.synchronize()
+        sharding.host_barrier() if world > 1 else None
+        t0 = time.perf_counter()
+        res = ftle_time_sweep(x, y, flows.double_gyre, spans, **kw)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        c5 = {"grid": [4096, 2048], "slices": 64, "slices_this_rank": len(res), "T": 20.0,
+              "percentile": 80, "wall_s_rank0": wall,
+              "ridge_lines_rank0": int(sum(len(v[3]) for v in res.values()))}
+        if rank == 0:
+            k = min(res)
+            sharding.set_distributed(False)
+            d = FTLE()
+            d.compute_device(x, y, flows.double_gyre, spans[k], edge_order=2, rtol=TOL, atol=TOL)
+            fm_s = d.flow_map[::32, ::64]
+            fm_o, _, _ = co.flow_map("double_gyre", po.flow_params("double_gyre"), x[::64], y[::32],
+                                     spans[k][0], spans[k][1], TOL, TOL, nthreads=host_cores())
+            same = bool(torch.equal(d.field_device, res[k][0]))
+            c5["oracle_check"] = {"sample": f"slice {k}: every 64th column / 32nd row, 4096 seeds, C oracle",
+                                  "max_abs_err_flow_map": float(np.abs(fm_s - fm_o).max()),
+                                  "sweep_field_equals_FTLE_compute_bitwise": same}
+        out["config5_time_sweep_64x4096x2048"] = c5
+    finally:
+        sharding.set_distributed(True)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -267,13 +409,17 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from dynlab_b200 import sharding
+    from dynlab_b200 import peer, sharding
     from dynlab_b200._engine import Engine
     from dynlab_b200.diagnostics import FTLE
     from dynlab_b200.flows import double_gyre
 
+    if world == 1:
+        peer.set_devices(None)  # N = 1 means one GPU even if the box shows more
     if args.halo:
         sharding.set_halo_mode(args.halo)
+    if args.transport:
+        sharding.set_transport(args.transport)
 
     eng = Engine.get()
     x, y = grid(1)
@@ -293,74 +439,152 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def total_launches():
+        return sum(e.launches for e in Engine._by_device.values())
+
     # FP64 peak of this GPU, measured in this run (roofline denominator for K1)
     peak_flops, _ = eng.dfma_peak(2048)
     peak_flops, _ = eng.dfma_peak(8192)
 
     # ---------------- device-resident loop: `value` ----------------
-    for _ in range(args.warmup):
-        diag.compute_device(x, y, double_gyre, T_SPAN, **kw)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    eng.profile = {}
-    launches0 = eng.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        diag.compute_device(x, y, double_gyre, T_SPAN, **kw)
-    e1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = eng.launches - launches0
-    prof, eng.profile = eng.profile, None
-    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in prof["rk45_flowmap"]]))
-    k2_ms = float(np.mean([a.elapsed_time(b) for a, b in prof["ftle_stencil"]]))
-    stats = eng.read_counters()  # last K1 launch on this rank
-    slab = sharding.partition(YDIM, world, rank)
-    ms_step = ms_total / args.steps
+    def time_value(steps, warmup, collect=False):
+        for _ in range(warmup):
+            diag.compute_device(x, y, double_gyre, T_SPAN, **kw)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and collect:
+            sampler.start()
+        eng.profile = {} if collect else None
+        l0 = total_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            out = diag.compute_device(x, y, double_gyre, T_SPAN, **kw)
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if (rank == 0 and collect) else None
+        ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        prof, eng.profile = eng.profile, None
+        return ms, out, prof, total_launches() - l0, clocks
+
+    ms_step, field_dev, prof, launches, clocks = time_value(args.steps, args.warmup, collect=True)
+    k1_ms = float(sum(a.elapsed_time(b) for a, b in prof["rk45_flowmap"])) / args.steps
+    k2_ms = float(sum(a.elapsed_time(b) for a, b in prof["ftle_stencil"])) / args.steps
+    k1_launches = len(prof["rk45_flowmap"]) / args.steps
+    diag._collect_stats() if world > 1 else None
+    stats = diag.stats if world > 1 else eng.read_counters()  # this rank's seeds, last step
     value = n_seeds / (ms_step * 1e-3)
+    group = peer.current_group(n_seeds) if world > 1 else None
+    bounds = diag._slab_bounds(group, diag._plan(x, y, double_gyre, T_SPAN, dict(rtol=TOL, atol=TOL))) \
+        if group is not None and sharding.transport() == "peer" else None
+    my_rows = (bounds[rank + 1] - bounds[rank]) if bounds else sharding.partition(YDIM, world, rank).rows
+
+    # result check of the device path: hash of the whole field + oracle error on a sample
+    value_sha = sha256_of(field_dev.cpu().numpy())
+    check = {"value_field_sha256": value_sha}
+    if rank == 0:
+        fm = diag.flow_map  # N > 1: one-sided read of the other ranks' rows (they wait below)
+        err, n_s = oracle_sample_error(fm[::64, ::64])
+        check.update({"flow_map_max_abs_err_vs_c_oracle": err,
+                      "oracle_sample": f"every 64th row and column ({n_s} seeds), oracle/c RK45 port"})
+        del fm
+    del diag.flow_map
+    barrier()
+
+    # the same step with NCCL carrying halo + gather after the kernels (round-1 data path), A/B
+    nccl_ms = None
+    if world > 1 and sharding.transport() == "peer":
+        sharding.set_transport("nccl")
+        nccl_ms, f_nccl, _, _, _ = time_value(max(3, args.steps // 2), 2)
+        check["nccl_transport_field_sha256"] = sha256_of(f_nccl.cpu().numpy())
+        del f_nccl
+        sharding.set_transport("peer")
+        barrier()
 
     # ---------------- end-to-end through the public API: `e2e` ----------------
-    def time_e2e(mode):
-        sharding.set_host_result(mode)
-        for _ in range(max(1, min(args.warmup, 2))):
-            diag.compute(x, y, double_gyre, T_SPAN, **kw)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            out = diag.compute(x, y, double_gyre, T_SPAN, **kw)
-        torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0) / args.steps
-        sharding.set_host_result("all")
-        return dt, out
-
-    # N = 1: private pinned copy, overlapped with K1.  N > 1: the ranks of the box share one
-    # pinned host segment — every rank returns the full field, each copies only its own rows.
-    e2e_s, field = time_e2e("all" if world == 1 else "shared")
-    e2e_all_s = e2e_rank0_s = None
-    if world > 1:  # same call with a private copy of the gathered field on every rank / rank 0
-        e2e_all_s, _ = time_e2e("all")
-        e2e_rank0_s, _ = time_e2e("rank0")
-    h2d = (XDIM + slab.rows) * 8 + 3 * 8 * (XDIM + YDIM)      # coordinates + stencil coefficients
+    for _ in range(max(1, min(args.warmup, 2))):
+        diag.compute(x, y, double_gyre, T_SPAN, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        field = diag.compute(x, y, double_gyre, T_SPAN, **kw)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+    check["e2e_field_sha256"] = sha256_of(np.ma.getdata(field))
+    h2d = (XDIM + my_rows) * 8 + 3 * 8 * (XDIM + YDIM)      # coordinates + stencil coefficients
     d2h = field.size * 8 + 64 * world                          # FTLE field (once) + counters
+    if world > 1:  # every rank must hold the same bytes
+        mine = torch.tensor([int(check["value_field_sha256"][:15], 16),
+                             int(check["e2e_field_sha256"][:15], 16)], dtype=torch.int64, device=eng.device)
+        lo, hi = mine.clone(), mine.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        check["all_ranks_hold_identical_fields"] = bool(torch.equal(lo, hi))
+    check["e2e_equals_value_field"] = check["e2e_field_sha256"] == value_sha
+    del field
+    barrier()
+
+    # ---------------- one plain process driving all N GPUs (rank 0; the others wait) ----------------
+    single = None
+    if world > 1 and not args.no_single_process:
+        if rank == 0:
+            sharding.set_distributed(False)
+            peer.set_devices(list(range(world)))
+            try:
+                d1 = FTLE()
+                for _ in range(2):
+                    d1.compute_device(x, y, double_gyre, T_SPAN, **kw)
+                for dv in range(world):
+                    torch.cuda.synchronize(dv)
+                n_sp = max(3, args.steps // 2)
+                t0 = time.perf_counter()
+                for _ in range(n_sp):
+                    fdev = d1.compute_device(x, y, double_gyre, T_SPAN, **kw)
+                for dv in range(world):
+                    torch.cuda.synchronize(dv)
+                sp_dev = (time.perf_counter() - t0) / n_sp
+                for _ in range(3):
+                    d1.compute(x, y, double_gyre, T_SPAN, **kw)
+                t0 = time.perf_counter()
+                for _ in range(n_sp):
+                    fh = d1.compute(x, y, double_gyre, T_SPAN, **kw)
+                sp_e2e = (time.perf_counter() - t0) / n_sp
+                single = {"devices": world, "steps": n_sp,
+                          "compute_device_ms_per_step": sp_dev * 1e3,
+                          "compute_host_field_ms_per_step": sp_e2e * 1e3,
+                          "seeds_per_s_e2e": n_seeds / sp_e2e,
+                          "field_sha256_device": sha256_of(fdev.cpu().numpy()),
+                          "field_sha256_host": sha256_of(np.ma.getdata(fh)),
+                          "what": "FTLE().compute in ONE process with no torch.distributed: one "
+                                  "host thread drives every GPU (dlb_peer_enable + the same "
+                                  "chunk pipeline); wall clock"}
+                single["equals_value_field"] = (single["field_sha256_device"] == value_sha
+                                                and single["field_sha256_host"] == value_sha)
+                del d1, fdev, fh
+            finally:
+                peer.set_devices("auto")
+                sharding.set_distributed(True)
+        sharding.host_barrier(timeout_s=600.0)  # host-side: the idle ranks' GPUs stay idle
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    configs = None
+    if not args.no_configs:
+        configs = extra_configs(eng, hbm_peak, world, rank, quick=world > 1)
+        barrier()
 
     if rank == 0:
         attempts = (stats["nfev"] - 2 * stats["seeds"]) / 6.0
         k1_flop = attempts * F_ATTEMPT + stats["seeds"] * F_SEED
         achieved = k1_flop / (k1_ms * 1e-3)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
         traffic = {}
         try:  # DRAM bytes per launch from the committed ncu --set full captures (1-GPU, config 3)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))
         except OSError:
             pass
 
@@ -368,59 +592,66 @@ def run_ours(args):
             t = traffic.get(kernel)
             return (t["dram_bytes_read"] + t["dram_bytes_write"]) if (t and world == 1) else None
 
-        k2_gbs = BYTES_PER_POINT_K2 * slab.rows * XDIM / (k2_ms * 1e-3) / 1e9
+        k2_gbs = BYTES_PER_POINT_K2 * my_rows * XDIM / (k2_ms * 1e-3) / 1e9
+        src = f"profiles/{TRAFFIC_FILE} (ncu --set full capture of this kernel at config 3, 1 GPU; not measured in this run)"
         line = {
             "metric": METRIC, "value": value, "unit": "seeds/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "FTLE double_gyre 8192x4096, t=(10,0), edge_order=2, "
-                                   "rtol=atol=1e-8 (BASELINE configs[2])",
-                       "parallelism": f"row slabs over {world} GPU(s); halo rows: "
-                                      f"{sharding.halo_mode()}; all-gather" if world > 1 else "single GPU",
-                       "l2": "inputs/outputs (537 MB flow map + 268 MB field per step) exceed "
-                             "the 126 MB L2; no flush needed",
-                       "integrator": {"mean_nfev_per_seed": stats["nfev"] / max(stats["seeds"], 1),
-                                      "rejected_attempts": stats["rejected"],
-                                      "failed_seeds": stats["failed"]}},
+            "data": "synthetic", "config": workload_config(world),
+            "parallelism": (f"{world} row slabs cut by integrator work ({bounds}), halo rows: "
+                            f"{sharding.halo_mode()}, transport: {sharding.transport()} "
+                            "(dlb_gather_rows pushes finished FTLE rows into every rank's field over "
+                            "NVLink peer memory while the next row chunk integrates)"
+                            if world > 1 else "single GPU"),
+            "integrator": {"mean_nfev_per_seed": stats["nfev"] / max(stats["seeds"], 1),
+                           "rejected_attempts": stats["rejected"], "failed_seeds": stats["failed"],
+                           "seeds_this_rank": stats["seeds"]},
+            "result_check": check,
             "e2e": {"value": n_seeds / e2e_s, "unit": "seeds/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
-                    "note": "public API FTLE().compute: host coordinates in, full host field out "
-                            "on EVERY rank (N=1: pinned D2H overlapped with K1 in row chunks; N>1: "
-                            "sharding.set_host_result('shared'), one pinned host segment mapped by "
-                            "all ranks, each rank streams its own rows into it through the same "
-                            "chunk pipeline, halo rows integrated locally)",
-                    "private_copy_per_rank_ms_per_step": None if e2e_all_s is None else e2e_all_s * 1e3,
-                    "rank0_host_only_ms_per_step": None if e2e_rank0_s is None else e2e_rank0_s * 1e3},
+                    "note": "public API FTLE().compute with library defaults: host coordinates in, "
+                            "full host field out on EVERY rank (pinned D2H of finished rows "
+                            "overlapped with K1 chunk by chunk; N>1: each rank streams its own "
+                            "rows into one pinned host segment mapped by all ranks)"},
             "gpu_launches": launches,
-            "kernels_ms": {"rk45_flowmap": k1_ms, "ftle_stencil": k2_ms},
+            "kernels_ms": {"rk45_flowmap": k1_ms, "ftle_stencil": k2_ms,
+                           "rk45_launches_per_step": k1_launches},
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved / 1e12, "peak": peak_flops / 1e12,
                          "unit": "TFLOP/s", "frac": achieved / peak_flops,
-                         "traffic": dram("rk45_kernel"),
+                         "traffic": dram("rk45_kernel"), "traffic_source": src,
                          "fp64_pipe_active_pct_ncu": (traffic.get("rk45_kernel") or {}).get(
                              "fp64_pipe_active_pct"),
+                         "fp64_pipe_active_pct_ncu_source": src,
                          "kernel": "rk45_kernel<double_gyre> (K1)",
                          "note": "algorithmic FLOP = attempts*872 + seeds*256 (SURVEY §8d model, "
-                                 "attempts counted by the kernel); peak = DFMA chain measured "
-                                 "in this run (dlb_dfma_peak), theoretical 37.2 TFLOP/s at "
-                                 "1965 MHz"},
+                                 "attempts counted by the kernel) / summed K1 launch time per step "
+                                 "(CUDA events); peak = DFMA chain measured in this run "
+                                 "(dlb_dfma_peak), theoretical 37.2 TFLOP/s at 1965 MHz"},
             "roofline_hbm": {"bound": "hbm", "achieved": k2_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": k2_gbs / hbm_peak,
-                             "traffic": dram("stencil_interior_kernel_ftle"),
-                             "kernel": "stencil_interior_kernel<FTLE> + stencil_edge_kernel (K2)",
+                             "traffic": dram("stencil_tma_kernel_ftle"), "traffic_source": src,
+                             "kernel": "stencil_tma_kernel<FTLE> + stencil_edge_kernel (K2)",
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         }
+        if nccl_ms is not None:
+            line["nccl_transport_ms_per_step"] = nccl_ms
+        if single is not None:
+            line["single_process"] = single
+        if configs is not None:
+            line["configs"] = configs
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_c_port()
-            # the reference's own Python path on the same cores (small strided samples):
-            # default LSODA integrator and the like-for-like scipy RK45 integrator
-            v_lsoda, _, smp, _ = reference_python_port(4096, "lsoda")
-            v_rk45, _, _, _ = reference_python_port(4096, "rk45")
-            line["cpu_baseline"]["python_reference_port"] = {
-                "lsoda_seeds_per_s": v_lsoda, "rk45_seeds_per_s": v_rk45, "sample": smp,
-                "what": "oracle/py_oracle.py: scipy per seed through a process pool over all "
-                        "cores + np.gradient + np.linalg.eig (what a dynlab user runs)"}
+            ref = reference_subprocess(max(2048, 600 * host_cores()), "lsoda")
+            cb = dict(ref["cpu_baseline"])
+            try:
+                rk = reference_subprocess(max(2048, 300 * host_cores()), "rk45")
+                cb["reference_with_scipy_rk45_integrator"] = {
+                    "value": rk["value"], "unit": "seeds/s", "sample": rk["cpu_baseline"]["sample"]}
+            except Exception as exc:  # noqa: BLE001 - a baseline leg must not kill the bench line
+                cb["reference_with_scipy_rk45_integrator"] = {"error": repr(exc)}
+            cb["c_port_rk45"] = cpu_baseline_c_port()
+            line["cpu_baseline"] = cb
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
@@ -436,7 +667,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--halo", choices=["exchange", "redundant"], default=None,
                     help="multi-GPU: how ranks obtain the halo rows (default: the library's)")
+    ap.add_argument("--transport", choices=["peer", "nccl"], default=None,
+                    help="multi-GPU: what carries halo + gather (default: the library's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the lines for BASELINE configs[1], [3], [4]")
+    ap.add_argument("--no-single-process", action="store_true",
+                    help="N>1: skip the one-process-drives-all-GPUs measurement")
     ap.add_argument("--ref-seeds", type=int, default=0,
                     help="--impl reference: seeds per step (default 600 per host core)")
     ap.add_argument("--ref-integrator", choices=["lsoda", "rk45"], default="lsoda",
