@@ -321,10 +321,13 @@ def extra_configs(eng, hbm_peak, world, rank, quick):
                                                            "GB_per_s": 8 * N * N / ms / 1e6}
             uh, vh = u.cpu().numpy(), v.cpu().numpy()
             d = AttractionRate()
-            d.compute(x, y, u=uh, v=vh, edge_order=2)
-            t0 = time.perf_counter()
-            att = d.compute(x, y, u=uh, v=vh, edge_order=2)
-            c2["e2e_host_uv_ms"] = (time.perf_counter() - t0) * 1e3
+            walls = []
+            for k in range(5):  # two warm-up calls (pinned staging buffers, allocator), median of 3
+                t0 = time.perf_counter()
+                att = d.compute(x, y, u=uh, v=vh, edge_order=2)
+                walls.append((time.perf_counter() - t0) * 1e3)
+            c2["e2e_host_uv_ms"] = float(np.median(walls[2:]))
+            c2["e2e_host_uv_ms_all_calls"] = walls
             c2["e2e_h2d_bytes"], c2["e2e_d2h_bytes"] = 2 * 8 * N * N, 8 * N * N
             sl = (slice(4000, 4064), slice(3000, 3064))
             ref = po.attraction_repulsion_rate(x[sl[1]], y[sl[0]], u=uh[sl], v=vh[sl], edge_order=2)
@@ -386,10 +389,13 @@ def extra_configs(eng, hbm_peak, world, rank, quick):
             fm_s = d.flow_map[::32, ::64]
             fm_o, _, _ = co.flow_map("double_gyre", po.flow_params("double_gyre"), x[::64], y[::32],
                                      spans[k][0], spans[k][1], TOL, TOL, nthreads=host_cores())
-            same = bool(torch.equal(d.field_device, res[k][0]))
+            dev = float((d.field_device - res[k][0]).abs().max().item())
             c5["oracle_check"] = {"sample": f"slice {k}: every 64th column / 32nd row, 4096 seeds, C oracle",
                                   "max_abs_err_flow_map": float(np.abs(fm_s - fm_o).max()),
-                                  "sweep_field_equals_FTLE_compute_bitwise": same}
+                                  "max_abs_diff_sweep_field_vs_FTLE_compute": dev,
+                                  "note": "the sweep's K2 also emits the eigenvector (LAPACK-"
+                                          "convention eigenvalue expression), FTLE.compute's does "
+                                          "not: fields agree to rounding, not bitwise"}
         out["config5_time_sweep_64x4096x2048"] = c5
     finally:
         sharding.set_distributed(True)
@@ -631,7 +637,7 @@ def run_ours(args):
                                  "(dlb_dfma_peak), theoretical 37.2 TFLOP/s at 1965 MHz"},
             "roofline_hbm": {"bound": "hbm", "achieved": k2_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": k2_gbs / hbm_peak,
-                             "traffic": dram("stencil_tma_kernel_ftle"), "traffic_source": src,
+                             "traffic": dram("stencil_interior_kernel_ftle"), "traffic_source": src,
                              "kernel": "stencil_tma_kernel<FTLE> + stencil_edge_kernel (K2)",
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         }
