@@ -343,6 +343,8 @@ class LagrangianDiagnostic2D(Diagnostic2D, ABC):
             self._integrate_rows(plan, slab.row0, slab.rows, own)
         self._counters_pending = slab.rows > 0
         self._counter_tensors = None
+        if not slab.rows:  # idle rank (more ranks than row pairs): nothing integrated here
+            self.stats = {"nfev": 0, "accepted": 0, "rejected": 0, "failed": 0, "seeds": 0}
         own = local[slab.halo_lo:slab.halo_lo + slab.rows]
         if size > 1:
             if not redundant:

@@ -195,13 +195,19 @@ class FTLE(LagrangianDiagnostic2D):
         exchange = sharding.halo_mode() == "exchange"
         gen = G.next_generation()
         row_b = xdim * 16
-        fm_sym = G.symmetric(("flow_map", gen % 2), max(max(s.nloc for s in slabs), 1) * row_b)
+        # rotating buffers are all created by the first call that needs them (allocation, IPC
+        # mapping and page-locking cost ~0.1 s per buffer: never inside a later, timed call)
+        fm_ring = [G.symmetric(("flow_map", k), max(max(s.nloc for s in slabs), 1) * row_b)
+                   for k in range(2)]
+        fm_sym = fm_ring[gen % 2]
         field_sym = host_np = host_t = None
         if target == "device":
-            field_sym = G.symmetric(("field", gen % peer.RESULT_DEPTH), ydim * xdim * 8)
+            ring = [G.symmetric(("field", k), ydim * xdim * 8) for k in range(peer.RESULT_DEPTH)]
+            field_sym = ring[gen % peer.RESULT_DEPTH]
         elif G.multiprocess:
-            host_np, host_t = sharding.shared_host_array(
-                (ydim, xdim), tag=("result", gen % peer.RESULT_DEPTH))
+            ring = [sharding.shared_host_array((ydim, xdim), tag=("result", k))
+                    for k in range(peer.RESULT_DEPTH)]
+            host_np, host_t = ring[gen % peer.RESULT_DEPTH]
         else:
             host_t = torch.empty((ydim, xdim), dtype=torch.float64, pin_memory=True)
             host_np = host_t.numpy()
