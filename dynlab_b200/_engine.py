@@ -50,6 +50,13 @@ class Engine:
         self._workspace = None
         self.counters = torch.zeros(nat.CNT_WORDS, dtype=torch.int64, device=self.device)
         self.copy_stream = torch.cuda.Stream(device=self.device)  # D2H overlapped with compute
+        # chunk pipeline of the Lagrangian path: K1 chunks alternate between the caller's stream
+        # and `alt_stream` (chunk c+1 fills the SMs as chunk c drains), K2 of a finished chunk
+        # runs on the high-priority `stencil_stream` as soon as CTA slots free up
+        self.alt_stream = torch.cuda.Stream(device=self.device)
+        self.stencil_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self._k1_ws = {}      # slot -> private K1 workspace (work counter + x, y rows)
+        self._pinned = {}     # coordinate bytes -> pinned host copy
         self.profile = None  # set to {} to collect (start, end) CUDA events per kernel name
         self.launches = 0    # kernels of libdynlab_b200.so launched through this engine
 
@@ -85,6 +92,29 @@ class Engine:
             grown = torch.empty(max(need, 1 << 22), dtype=torch.uint8, device=self.device)
             self._workspace = grown
         return self._workspace.data_ptr(), self._workspace.numel()
+
+    def k1_workspace(self, slot: int, xdim: int, rows: int):
+        """Private workspace of K1 launches that may overlap other launches (chunk pipeline)."""
+        need = int(nat.lib.dlb_workspace_bytes(xdim, rows))
+        ws = self._k1_ws.get(slot)
+        if ws is None or ws.numel() < need:
+            ws = self._k1_ws[slot] = torch.empty(max(need, 1 << 20), dtype=torch.uint8,
+                                                 device=self.device)
+        return ws.data_ptr(), ws.numel()
+
+    def pinned_coord(self, a: np.ndarray) -> np.ndarray:
+        """Page-locked copy of a coordinate vector (cached by value).  The library uploads x and
+        the chunk's y rows on every K1 launch; from pageable memory that cudaMemcpyAsync first
+        waits for the stream to drain, from pinned memory it is a plain enqueue."""
+        key = a.tobytes()
+        hit = self._pinned.get(key)
+        if hit is None:
+            if len(self._pinned) >= 16:
+                self._pinned.clear()
+            t = torch.empty(max(a.size, 1), dtype=_F64, pin_memory=True)
+            t[:a.size].copy_(torch.from_numpy(a))
+            hit = self._pinned[key] = (t, t.numpy()[:a.size])
+        return hit[1]
 
     def empty(self, *shape, dtype=_F64):
         return torch.empty(*shape, dtype=dtype, device=self.device)
@@ -234,13 +264,19 @@ class Engine:
     # -- K1 ---------------------------------------------------------------------------
     def flow_map(self, flow_id, params, x, y, row0, rows, t0, tf, rtol, atol,
                  max_step=math.inf, first_step=0.0, out=None, nfev=None, status=None,
-                 counters=None):
-        """Enqueue K1 for rows [row0, row0+rows) of the grid; returns the [rows, xdim, 2] tensor."""
+                 counters=None, ws_slot=None):
+        """Enqueue K1 for rows [row0, row0+rows) of the grid; returns the [rows, xdim, 2] tensor.
+        ``ws_slot``: use that private K1 workspace instead of the engine's shared one (launches
+        that run concurrently with other launches of this engine)."""
         xdim = len(x)
         with torch.cuda.device(self.device):
             if out is None:
                 out = self.empty(rows, xdim, 2)
-            ws, wsz = self.workspace(xdim, max(len(y), rows))
+            if ws_slot is None:
+                ws, wsz = self.workspace(xdim, max(len(y), rows))
+            else:
+                ws, wsz = self.k1_workspace(ws_slot, xdim, rows)
+                x, y = self.pinned_coord(x), self.pinned_coord(y)
             p = nat.darray(params)
             with self._timed("rk45_flowmap"):
               nat.check(nat.lib.dlb_flowmap_rk45(

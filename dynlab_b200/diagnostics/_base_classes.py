@@ -275,14 +275,15 @@ class LagrangianDiagnostic2D(Diagnostic2D, ABC):
         return dict(fid=fid, params=params, t0=t0, tf=tf, rtol=kw["rtol"], atol=float(atol),
                     max_step=kw["max_step"], first_step=first or 0.0)
 
-    def _integrate_rows(self, plan, row0, rows, out, counters=None, eng=None, y=None, nfev=None):
+    def _integrate_rows(self, plan, row0, rows, out, counters=None, eng=None, y=None, nfev=None,
+                        ws_slot=None):
         """Enqueue K1 for rows [row0, row0 + rows) of the grid into ``out`` ([rows, xdim, 2])
         on ``eng``'s device (default: the current one)."""
         eng = eng or Engine.get()
         return eng.flow_map(plan["fid"], plan["params"], self._xf, self._yf if y is None else y,
                             row0, rows, plan["t0"], plan["tf"], plan["rtol"], plan["atol"],
                             plan["max_step"], plan["first_step"], out=out, counters=counters,
-                            nfev=nfev)
+                            nfev=nfev, ws_slot=ws_slot)
 
     # -- cost-weighted row slabs ------------------------------------------------------------
     _row_cost_cache: dict = {}

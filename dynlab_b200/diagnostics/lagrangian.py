@@ -51,7 +51,17 @@ def pipeline_schedule(lo, hi, own0, own1, ydim, edge_order, chunks, last_fractio
     row an output row's stencil reads - its neighbours, and rows 0..2 / ydim-3..ydim-1 for the
     one-sided edge_order-2 formulas at the global edges - lies in [lo, r1)."""
     nloc = hi - lo
-    if chunks > 1 and nloc >= 64 * chunks:
+    if isinstance(chunks, (tuple, list)):
+        # explicit chunk sizes as fractions of the rows (overlapped pipeline: large chunks
+        # first, the last two small); chunks below 32 rows are merged into their predecessor
+        cum, bounds = 0.0, [lo]
+        for fr in chunks[:-1]:
+            cum += fr / float(sum(chunks))
+            b = lo + int(round(nloc * cum))
+            if b - bounds[-1] >= 32 and hi - b >= 32:
+                bounds.append(b)
+        bounds.append(hi)
+    elif chunks > 1 and nloc >= 64 * chunks:
         last = max(64, nloc // last_fraction)
         bounds = [lo + (nloc - last) * c // (chunks - 1) for c in range(chunks)] + [hi]
     else:
@@ -105,8 +115,10 @@ class FTLE(LagrangianDiagnostic2D):
         group = self._group(np.size(x) * np.size(y))
         if group is not None:  # several GPUs: row slabs, peer-memory data path (csrc/peer.cu)
             return self._compute_group(group, self._plan(x, y, f, t, kwargs), t, edge_order, "host")
-        if (sharding.world()[1] == 1 and self.pipeline_chunks > 1
-                and np.size(y) >= 64 * self.pipeline_chunks and np.size(x) * np.size(y) >= (1 << 22)):
+        n_chunks = len(self.pipeline_chunks) if isinstance(self.pipeline_chunks, (tuple, list)) \
+            else self.pipeline_chunks
+        if (sharding.world()[1] == 1 and n_chunks > 1
+                and np.size(y) >= 64 * n_chunks and np.size(x) * np.size(y) >= (1 << 22)):
             return self._compute_pipelined(self._plan(x, y, f, t, kwargs), t, edge_order)
         # one device, or sharding.set_transport("nccl"): kernels, then NCCL halo + all-gathers,
         # then one device-to-host copy of the gathered field per rank
@@ -236,13 +248,13 @@ class FTLE(LagrangianDiagnostic2D):
             runs.append(dict(m=m, s=s, steps=steps, tail=tail, fm=fm, out=out, out_row0=out_row0,
                              counters=counters, main=main, pushes=0))
 
-        def ship(run, a, b, last):
-            """FTLE rows [a, b) of this member were just enqueued on its main stream: send
-            them on their way on the copy stream."""
+        def ship(run, a, b, last, after=None):
+            """FTLE rows [a, b) of this member were just enqueued on stream ``after`` (default:
+            its main stream): send them on their way on the copy stream."""
             m, eng = run["m"], run["m"].engine
             with torch.cuda.device(m.device):
                 ev = torch.cuda.Event()
-                ev.record(run["main"])
+                ev.record(after or run["main"])
                 eng.copy_stream.wait_event(ev)
                 if target == "device":
                     run["pushes"] += 1
@@ -263,6 +275,15 @@ class FTLE(LagrangianDiagnostic2D):
 
         # chunk-major over the local members, so that every device has work queued before the
         # host moves on to the next chunk
+        overlap = bool(self.overlap_chunks)
+        for run in runs:
+            eng = run["m"].engine
+            run["k1_streams"] = [run["main"], eng.alt_stream] if overlap else [run["main"]]
+            run["k2_stream"] = eng.stencil_stream if overlap else run["main"]
+            run["k1_events"] = []
+            if overlap:
+                eng.alt_stream.wait_stream(run["main"])
+                eng.stencil_stream.wait_stream(run["main"])
         for c in range(max([len(r["steps"]) for r in runs] + [0])):
             for run in runs:
                 if c >= len(run["steps"]):
@@ -270,13 +291,31 @@ class FTLE(LagrangianDiagnostic2D):
                 m, s = run["m"], run["s"]
                 r0, r1, done, upto = run["steps"][c]
                 lo = s.lo  # fm row 0 is global row s.lo (halo slot included)
-                with torch.cuda.device(m.device):
+                k1s = run["k1_streams"][c % len(run["k1_streams"])]
+                with torch.cuda.device(m.device), torch.cuda.stream(k1s):
+                    # overlap: K1 of chunk c+1 (other stream, private workspace) takes over the
+                    # SMs CTA by CTA as chunk c drains - no tail bubble between chunks
                     self._integrate_rows(plan, r0, r1 - r0, run["fm"][r0 - lo:r1 - lo],
-                                         counters=run["counters"][c], eng=m.engine)
+                                         counters=run["counters"][c], eng=m.engine,
+                                         ws_slot=(c % 2) if overlap else None)
+                    if overlap:
+                        ev = torch.cuda.Event()
+                        ev.record(k1s)
+                        run["k1_events"].append(ev)
                 if upto > done:
-                    stencil(run, run["steps"][0][0], r1, done, upto)
+                    k2s = run["k2_stream"]
+                    if overlap:
+                        for ev in run["k1_events"][-2:]:
+                            k2s.wait_event(ev)
+                    with torch.cuda.device(m.device), torch.cuda.stream(k2s):
+                        stencil(run, run["steps"][0][0], r1, done, upto)
                     last = c == len(run["steps"]) - 1 and not run["tail"]
-                    ship(run, done, upto, last)
+                    ship(run, done, upto, last, k2s)
+        if overlap:
+            for run in runs:
+                eng = run["m"].engine
+                run["main"].wait_stream(eng.alt_stream)
+                run["main"].wait_stream(eng.stencil_stream)
         # 1-row halo exchange (dlb_halo_exchange: every member pushes first, then waits), then the
         # rows that were waiting for it
         for run in runs:
@@ -345,6 +384,9 @@ class FTLE(LagrangianDiagnostic2D):
         return b
 
     weighted_slabs = True  # cut the slabs by integrator work instead of by rows (large grids)
+    # K1 chunks on alternating streams (chunk c+1 fills the SMs as chunk c drains), K2 on its own
+    # high-priority stream; False: everything in order on one stream (K2 between the chunks)
+    overlap_chunks = False
 
     def _gather_flow_map(self, G, fm_sym, slabs, m):
         """The reference's `flow_map` attribute (R:_base_classes.py:187): collected on demand by

@@ -1021,9 +1021,10 @@ def test_single_process_group_matches_single_device(dl):
             peer.set_devices(spec)
             for halo in ("exchange", "redundant"):
                 sharding.set_halo_mode(halo)
-                for weighted in (True, False):
+                for weighted, overlap, chunks in ((True, False, 4), (False, True, 4),
+                                                  (True, True, (0.45, 0.45, 0.07, 0.03))):
                     d = D.FTLE()
-                    d.weighted_slabs = weighted
+                    d.weighted_slabs, d.overlap_chunks, d.pipeline_chunks = weighted, overlap, chunks
                     f = np.ma.getdata(d.compute(x, y, fl.double_gyre, t, **kw))
                     assert np.array_equal(f, f1), (nx, ny, halo, weighted)
                     if halo == "exchange":
