@@ -324,6 +324,25 @@ class Engine:
                 xi.data_ptr() if xi is not None else None, xi_mode, ws, wsz, self.stream()))
         return out, xi
 
+    def ftle_stencil_gather(self, fm_local, grow0, x, y, edge_order, t_span, out_row0, out_rows,
+                            out, peer_ptrs, flag_ptrs, flag_value):
+        """K2 fused with the row gather (``dlb_ftle_stencil_gather``): values go to ``out`` and to
+        the raw device addresses ``peer_ptrs`` (other GPUs' buffers, same row offset), then
+        ``flag_value`` is released at ``flag_ptrs``."""
+        xdim, ydim = len(x), len(y)
+        nloc = fm_local.shape[0]
+        peers = (C.c_void_p * max(len(peer_ptrs), 1))(*peer_ptrs)
+        flags = (C.c_void_p * max(len(flag_ptrs), 1))(*flag_ptrs)
+        with torch.cuda.device(self.device):
+            ws, wsz = self.workspace(xdim, ydim)
+            with self._timed("ftle_stencil", 3):
+              nat.check(nat.lib.dlb_ftle_stencil_gather(
+                fm_local.data_ptr(), nloc, grow0, nat.dptr(x), xdim, nat.dptr(y), ydim,
+                int(edge_order), float(t_span), out_row0, out_rows,
+                out.data_ptr() if out_rows else fm_local.data_ptr(), peers, len(peer_ptrs), flags,
+                len(flag_ptrs), int(flag_value), ws, wsz, self.stream()))
+        return out
+
     # -- K3 ---------------------------------------------------------------------------
     def euler_stencil(self, mode, u_local, v_local, grow0, x, y, edge_order, out_row0, out_rows,
                       negate=False, xi_mode=nat.XI_NONE):

@@ -59,6 +59,9 @@ SIGNATURES = {
     "dlb_gather_rows": (_i, [_vp, _sz, C.POINTER(_vp), _i, C.POINTER(_vp), C.c_uint64, _vp]),
     "dlb_halo_exchange": (_i, [_vp, _sz, _i64, _i64, _vp, _vp, _vp, _vp, C.c_uint64, _vp]),
     "dlb_wait_flags": (_i, [_vp, _i, C.c_uint64, _d, _vp, _vp]),
+    "dlb_ftle_stencil_gather": (_i, [_vp, _i64, _i64, _dp, _i64, _dp, _i64, _i, _d, _i64, _i64,
+                                     _vp, C.POINTER(_vp), _i, C.POINTER(_vp), _i, C.c_uint64,
+                                     _vp, _sz, _vp]),
 }
 
 MAX_PEERS = 16

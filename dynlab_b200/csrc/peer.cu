@@ -76,6 +76,11 @@ int push_flags(uint64_t* const* d_flags, int n, uint64_t value, cudaStream_t str
 
 }  // namespace
 
+// used by dlb_ftle_stencil_gather (stencil.cu): the release that follows the fused kernels
+int dlb_push_flags_after(uint64_t* const* d_flags, int n, uint64_t value, cudaStream_t stream) {
+  return push_flags(d_flags, n, value, stream);
+}
+
 extern "C" int dlb_device_count(int* n) {
   if (!n) {
     dlb_set_error("dlb_device_count: null pointer");

@@ -1011,6 +1011,48 @@ extern "C" int dlb_ftle_stencil(const double* d_flow_map, int64_t nloc, int64_t 
   return launch_stencil<KIND_FTLE, 0, true>(P, ld, stream);
 }
 
+// K2 fused with the row gather (csrc/peer.cu has the DMA flavour): same kernels, the epilogue
+// stores every value locally and into the peers' buffers, then one warp releases the flags.
+int dlb_push_flags_after(uint64_t* const* d_flags, int n, uint64_t value, cudaStream_t stream);
+
+extern "C" int dlb_ftle_stencil_gather(const double* d_flow_map, int64_t nloc, int64_t grow0,
+                                       const double* h_x, int64_t xdim, const double* h_y,
+                                       int64_t ydim, int edge_order, double t_span,
+                                       int64_t out_row0, int64_t out_rows, double* d_ftle,
+                                       double* const* d_peer_ftle, int n_peer,
+                                       uint64_t* const* d_flags, int n_flags, uint64_t flag_value,
+                                       void* d_workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!d_flow_map || !d_ftle || n_peer < 0 || n_peer > DLB_MAX_PEERS || (n_peer && !d_peer_ftle) ||
+      n_flags < 0 || n_flags > DLB_MAX_PEERS || (n_flags && !d_flags)) {
+    dlb_set_error("dlb_ftle_stencil_gather: bad argument");
+    return DLB_ERR_ARG;
+  }
+  StencilParams P;
+  memset(&P, 0, sizeof(P));
+  int rc = setup_axes(P, h_x, xdim, h_y, ydim, edge_order, d_workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  P.nloc = nloc;
+  P.grow0 = grow0;
+  P.out_row0 = out_row0;
+  P.out_rows = out_rows;
+  rc = check_slab(P, ydim);
+  if (rc) return rc;
+  if (out_rows > 0) {
+    P.fm = (const double2*)d_flow_map;
+    P.field = d_ftle;
+    P.xi_mode = DLB_XI_NONE;
+    P.scale = 1.0 / (2.0 * fabs(t_span));  // lagrangian.py:71
+    for (int k = 0; k < n_peer; ++k)
+      if (d_peer_ftle[k] && d_peer_ftle[k] != d_ftle) P.peer[P.npeer++] = d_peer_ftle[k];
+    LoaderAoS ld{P.fm, xdim};
+    rc = P.npeer ? launch_stencil<KIND_FTLE, FTLE_PUSH, false>(P, ld, stream)
+                 : launch_stencil<KIND_FTLE, FTLE_PLAIN, false>(P, ld, stream);
+    if (rc) return rc;
+  }
+  return dlb_push_flags_after(d_flags, n_flags, flag_value, stream);
+}
+
 extern "C" int dlb_euler_stencil(int mode, const double* d_u, const double* d_v, int64_t nloc,
                                  int64_t grow0, const double* h_x, int64_t xdim, const double* h_y,
                                  int64_t ydim, int edge_order, int64_t out_row0, int64_t out_rows,

@@ -47,6 +47,10 @@ struct StencilParams {
   int use_threshold;
   int xi_mode;
   int negate;
+  // FTLE with MODE == FTLE_PUSH (K2 fused with the row gather): every value is also stored at
+  // the same offset of these buffers (peer GPUs' copies of the field, addressed over NVLink)
+  int npeer;
+  double* peer[DLB_MAX_PEERS];
 };
 
 }  // namespace dlbst
@@ -63,6 +67,17 @@ constexpr int ST_ROWS = 32;  // rows per warp task
 
 
 enum { KIND_FTLE = 0, KIND_EULER = 1 };
+// MODE of a KIND_FTLE kernel: plain, or with the peer stores of the fused gather
+enum { FTLE_PLAIN = 0, FTLE_PUSH = 1 };
+
+template <int KIND, int MODE>
+__device__ __forceinline__ void store_ftle(const StencilParams& P, long long o, double out) {
+  P.field[o] = out;
+  if constexpr (KIND == KIND_FTLE && MODE == FTLE_PUSH) {
+#pragma unroll 1
+    for (int k = 0; k < P.npeer; ++k) P.peer[k][o] = out;  // posted NVLink writes
+  }
+}
 
 // ---- symmetric 2x2 eigen helpers ----
 
@@ -383,7 +398,7 @@ __device__ __forceinline__ void emit(const StencilParams& P, double2 C, double d
                            : log(lam));
     else if (lam != lam)
       out = lam;  // NaN propagates like np.log
-    P.field[o] = out;
+    store_ftle<KIND, MODE>(P, o, out);
     if (XI) P.xi[o] = make_double2(vx, vy);
   } else {
     // S = 0.5 (G + G^T), G = [[dudx, dudy], [dvdx, dvdy]]   (eulerian.py:52-53)
@@ -437,7 +452,7 @@ __device__ __forceinline__ void emit_pred(const StencilParams& P, double2 C, dou
     double fl = fast_log_ge1_tab(lam, logtab);       // meaningless below 1, selected away
     fl = (lam < CUDART_INF) ? fl : lam;              // inf -> inf, NaN -> NaN like np.log
     const double out = (lam >= 1.0) ? P.scale * fl : ((lam != lam) ? lam : 0.0);
-    if (store) P.field[o] = out;
+    if (store) store_ftle<KIND, MODE>(P, o, out);
   } else if constexpr (KIND == KIND_EULER && !XI &&
                        (MODE == DLB_EULER_S_MIN || MODE == DLB_EULER_S_MAX)) {
     const double a = d0dx, d = d1dy, b = 0.5 * (d0dy + d1dx);

@@ -291,13 +291,15 @@ class LagrangianDiagnostic2D(Diagnostic2D, ABC):
     PILOT_MIN_SEEDS = 1 << 20
 
     def _row_costs(self, plan, eng):
-        """Per-row work estimate for ``sharding.weighted_bounds``: the integrator attempts of
-        every (ydim / PILOT_ROWS)-th row, measured once per (flow, t, tolerances, grid) by a
-        pilot run of K1 with per-seed ``nfev`` output (1/64 of the grid, ~1 ms at config 3) and
-        interpolated in between.  A warp advances until its slowest lane is done, so a row
-        costs the sum over its 32-seed groups of the largest nfev in the group.  The flow's own
-        imbalance (2.5 % between equal slabs of the double gyre at 8 GPUs) is what this
-        removes; returns None for grids too small to matter."""
+        """Per-row work estimate for ``sharding.weighted_bounds``, measured once per (flow, t,
+        tolerances, grid) by a pilot run of K1 with per-seed ``nfev`` output over 1/64 of the
+        seeds (~1 ms at config 3): in EVERY row, a few of its 32-seed groups (columns staggered
+        from row to row).  A warp advances until its slowest lane is done, so a group costs its
+        largest nfev; a row costs the mean over its sampled groups.  Sampling every row matters:
+        the double gyre's cost per row rises by 5 % over the last 200 rows of config 3, which a
+        every-64th-row pilot misses (it left the last of 8 slabs 1.9 % heavy; this one: 0.1 %).
+        Removes the flow's own imbalance (4 % between equal slabs at 8 GPUs); returns None for
+        grids too small to matter."""
         ydim, xdim = self.ydim, self.xdim
         if ydim * xdim < self.PILOT_MIN_SEEDS or ydim < 4 * self.PILOT_ROWS:
             return None
@@ -306,18 +308,20 @@ class LagrangianDiagnostic2D(Diagnostic2D, ABC):
                self._yf.tobytes())
         cost = self._row_cost_cache.get(key)
         if cost is None:
-            idx = np.unique(np.append(np.arange(0, ydim, max(1, ydim // self.PILOT_ROWS)), ydim - 1))
-            ys = np.ascontiguousarray(self._yf[idx])
+            groups = -(-xdim // 32)
+            per_row = max(1, min(groups, round(groups / 64)))
+            rows = np.arange(ydim)[:, None, None]
+            g = (7 * rows + np.arange(per_row)[None, :, None] * (groups // per_row)) % groups
+            cols = np.minimum(g * 32 + np.arange(32)[None, None, :], xdim - 1)
+            seeds = np.stack([self._xf[cols], np.broadcast_to(self._yf[rows], cols.shape)], axis=-1)
             with torch.cuda.device(eng.device):
-                nfev = torch.zeros(len(idx), xdim, dtype=torch.int32, device=eng.device)
-                tmp = eng.empty(len(idx), xdim, 2)
-                self._integrate_rows(plan, 0, len(idx), tmp, eng=eng, y=ys, nfev=nfev,
-                                     counters=torch.zeros(nat.CNT_WORDS, dtype=torch.int64,
-                                                          device=eng.device))
-                pad = (-xdim) % 32
-                grp = torch.nn.functional.pad(nfev, (0, pad)).view(len(idx), -1, 32)
-                per_row = grp.max(dim=2).values.sum(dim=1).double().cpu().numpy()
-            cost = np.interp(np.arange(ydim), idx, per_row)
+                sd = torch.from_numpy(np.ascontiguousarray(seeds.reshape(-1, 2))).to(eng.device)
+                nfev = torch.zeros(sd.shape[0], dtype=torch.int32, device=eng.device)
+                eng.rk45_endpoints(plan["fid"], plan["params"], sd, plan["t0"], plan["tf"],
+                                   plan["rtol"], plan["atol"], plan["max_step"],
+                                   plan["first_step"], nfev=nfev)
+                cost = nfev.view(ydim, per_row, 32).max(dim=2).values.double().mean(dim=1)
+                cost = cost.cpu().numpy()
             if len(self._row_cost_cache) > 32:
                 self._row_cost_cache.clear()
             self._row_cost_cache[key] = cost

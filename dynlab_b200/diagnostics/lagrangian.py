@@ -261,6 +261,8 @@ class FTLE(LagrangianDiagnostic2D):
                     value = gen * peer.GEN_STRIDE + (peer.DONE if last else min(run["pushes"], peer.DONE - 1))
                     G.push_rows(m, field_sym, a * xdim * 8, (b - a) * xdim * 8, value,
                                 eng.copy_stream.cuda_stream, dests)
+                    run["pushed"] = torch.cuda.Event()
+                    run["pushed"].record(eng.copy_stream)
                 elif b > a:
                     with torch.cuda.stream(eng.copy_stream):
                         r0 = run["out_row0"]
@@ -272,6 +274,28 @@ class FTLE(LagrangianDiagnostic2D):
             with torch.cuda.device(run["m"].device):
                 eng.ftle_stencil(run["fm"][g0 - lo:g1 - lo], g0, self._xf, self._yf, edge_order,
                                  t_span, a, b - a, out=run["out"][a - r0:b - r0])
+
+        def produce(run, g0, g1, a, b, last, fused, stream):
+            """K2 for FTLE rows [a, b) on ``stream`` and their departure.  ``fused`` (device
+            target, the last rows of a slab): dlb_ftle_stencil_gather - the epilogue itself
+            stores into the other members' fields over NVLink and the flags follow the kernel,
+            no copy-engine pass after it."""
+            m, eng = run["m"], run["m"].engine
+            if not (fused and target == "device"):
+                with torch.cuda.device(m.device), torch.cuda.stream(stream):
+                    stencil(run, g0, g1, a, b)
+                ship(run, a, b, last, stream)
+                return
+            run["pushes"] += 1
+            value = gen * peer.GEN_STRIDE + (peer.DONE if last else min(run["pushes"], peer.DONE - 1))
+            peers, flags = G.push_targets(m, field_sym, a * xdim * 8, dests)
+            lo = run["s"].lo
+            with torch.cuda.device(m.device), torch.cuda.stream(stream):
+                if run.get("pushed") is not None:  # the flag must not overtake earlier DMA pushes
+                    stream.wait_event(run["pushed"])
+                eng.ftle_stencil_gather(run["fm"][g0 - lo:g1 - lo], g0, self._xf, self._yf,
+                                        edge_order, t_span, a, b - a, run["out"][a:b], peers,
+                                        flags, value)
 
         # chunk-major over the local members, so that every device has work queued before the
         # host moves on to the next chunk
@@ -307,10 +331,10 @@ class FTLE(LagrangianDiagnostic2D):
                     if overlap:
                         for ev in run["k1_events"][-2:]:
                             k2s.wait_event(ev)
-                    with torch.cuda.device(m.device), torch.cuda.stream(k2s):
-                        stencil(run, run["steps"][0][0], r1, done, upto)
-                    last = c == len(run["steps"]) - 1 and not run["tail"]
-                    ship(run, done, upto, last, k2s)
+                    left = len(run["steps"]) - 1 - c  # chunks still to come
+                    last = left == 0 and not run["tail"]
+                    produce(run, run["steps"][0][0], r1, done, upto, last,
+                            left < self.fused_gather_chunks, k2s)
         if overlap:
             for run in runs:
                 eng = run["m"].engine
@@ -326,8 +350,7 @@ class FTLE(LagrangianDiagnostic2D):
             if run["tail"]:
                 G.halo_wait(m, slabs, gen, run["main"].cuda_stream)
                 for k, (a, b) in enumerate(run["tail"]):
-                    stencil(run, s.lo, s.hi, a, b)
-                    ship(run, a, b, k == len(run["tail"]) - 1)
+                    produce(run, s.lo, s.hi, a, b, k == len(run["tail"]) - 1, True, run["main"])
             elif not s.rows:
                 ship(run, 0, 0, True)  # nothing to send: still tell the others we are done
 
@@ -361,8 +384,9 @@ class FTLE(LagrangianDiagnostic2D):
         """Row boundaries of the members' slabs: equal work (pilot run, `_row_costs`) when the
         grid is large enough to care, equal rows otherwise.  With one process per GPU rank 0's
         estimate is broadcast once per (flow, t, grid) so that all ranks cut at the same rows."""
-        key = ("bounds", G.size, plan["fid"], tuple(plan["params"]), plan["t0"], plan["tf"],
-               plan["rtol"], plan["atol"], self._xf.tobytes(), self._yf.tobytes())
+        key = ("bounds", G.size, bool(self.weighted_slabs), plan["fid"], tuple(plan["params"]),
+               plan["t0"], plan["tf"], plan["rtol"], plan["atol"], self._xf.tobytes(),
+               self._yf.tobytes())
         b = self._row_cost_cache.get(key)
         if b is None:
             b = sharding.uniform_bounds(self.ydim, G.size)
@@ -387,6 +411,10 @@ class FTLE(LagrangianDiagnostic2D):
     # K1 chunks on alternating streams (chunk c+1 fills the SMs as chunk c drains), K2 on its own
     # high-priority stream; False: everything in order on one stream (K2 between the chunks)
     overlap_chunks = False
+    # device result: the K2 launches of this many last chunks (and of the rows that wait for a
+    # halo exchange) store straight into the other GPUs' fields (dlb_ftle_stencil_gather);
+    # earlier chunks are pushed by a copy engine behind the integrator
+    fused_gather_chunks = 1
 
     def _gather_flow_map(self, G, fm_sym, slabs, m):
         """The reference's `flow_map` attribute (R:_base_classes.py:187): collected on demand by

@@ -153,6 +153,15 @@ class Group:
                                               int(flag_value), stream))
         m.engine.launches += 1
 
+    def push_targets(self, m: Member, buf: SymBuf, byte_offset: int, dests=None):
+        """(peer addresses, flag addresses) for ``dlb_ftle_stencil_gather``: where member m's rows
+        at ``byte_offset`` live in the other destinations' blocks, and every destination's gather
+        flag of source ``m.rank`` (own included)."""
+        row, frow = buf.addr[m.rank], self.flags.addr[m.rank]
+        on = sorted(set(range(self.size) if dests is None else dests))
+        return ([row[j] + byte_offset for j in on if j != m.rank],
+                [frow[j] + 8 * m.rank for j in on])
+
     def wait_gathered(self, m: Member, generation: int, stream) -> None:
         """``dlb_wait_flags`` on member m's stream: every member's DONE flag of this generation."""
         base = self.flags.addr[m.rank][m.rank]

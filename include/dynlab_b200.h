@@ -270,6 +270,18 @@ int dlb_gather_rows(const void* d_src, size_t bytes, void* const* d_dst, int n_d
 int dlb_halo_exchange(const void* d_local, size_t row_bytes, int64_t first_own, int64_t last_own,
                       void* d_up_slot, void* d_down_slot, uint64_t* d_up_flag,
                       uint64_t* d_down_flag, uint64_t flag_value, void* stream);
+/* K2 fused with the row gather: dlb_ftle_stencil (xi_mode NONE) whose epilogue stores every FTLE
+ * value into d_ftle AND at the same offset of the n_peer buffers d_peer_ftle[k] (the other GPUs'
+ * copies of these rows, i.e. their field base + out_row0 * xdim; NULL or == d_ftle entries are
+ * skipped) — NVLink stores issued by the SMs as the values are produced, no copy afterwards —
+ * and then releases `flag_value` at the n_flags flags like dlb_gather_rows.  Used for the last
+ * rows of a slab, where a copy engine pass after the kernel would be exposed latency. */
+int dlb_ftle_stencil_gather(const double* d_flow_map, int64_t nloc, int64_t grow0,
+                            const double* h_x, int64_t xdim, const double* h_y, int64_t ydim,
+                            int edge_order, double t_span, int64_t out_row0, int64_t out_rows,
+                            double* d_ftle, double* const* d_peer_ftle, int n_peer,
+                            uint64_t* const* d_flags, int n_flags, uint64_t flag_value,
+                            void* d_workspace, size_t workspace_bytes, void* stream);
 /* Receive side of both: enqueue a one-warp kernel that polls d_flags[0..n) (n <= 32, this
  * device's memory) until every one is >= min_value (acquire at system scope), so later work
  * on `stream` sees the rows.  Bounded: after timeout_s seconds it gives up and stores

@@ -1025,6 +1025,7 @@ def test_single_process_group_matches_single_device(dl):
                                                   (True, True, (0.45, 0.45, 0.07, 0.03))):
                     d = D.FTLE()
                     d.weighted_slabs, d.overlap_chunks, d.pipeline_chunks = weighted, overlap, chunks
+                    d.fused_gather_chunks = 2 if overlap else (0 if weighted else 1)
                     f = np.ma.getdata(d.compute(x, y, fl.double_gyre, t, **kw))
                     assert np.array_equal(f, f1), (nx, ny, halo, weighted)
                     if halo == "exchange":

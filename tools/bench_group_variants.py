@@ -34,13 +34,15 @@ kw = dict(edge_order=2, rtol=1e-8, atol=1e-8)
 eng = Engine.get()
 
 
-def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=True, overlap=None):
+def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=True, overlap=None,
+        fused=1):
     sharding.set_transport(transport)
     sharding.set_halo_mode(halo)
     d = FTLE()
     d.pipeline_chunks, d.pipeline_last_fraction, d.weighted_slabs = chunks, frac, weighted
     if overlap is not None:
         d.overlap_chunks = overlap
+    d.fused_gather_chunks = fused
     for _ in range(3):
         d.compute_device(x, y, double_gyre, (10, 0), **kw)
     dist.barrier()
@@ -62,7 +64,7 @@ def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=Tru
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     out = {"variant": name, "transport": transport, "halo": halo, "chunks": list(chunks) if isinstance(chunks, tuple) else chunks, "last_fraction": frac,
-           "weighted": weighted, "overlap": overlap, "ms_per_step": float(tmax[0]),
+           "weighted": weighted, "overlap": overlap, "fused": fused, "ms_per_step": float(tmax[0]),
            "k1_ms_max_rank": float(tmax[1]), "k1_ms_min_rank": float(tmin[1]),
            "sha": hashlib.sha256(f.cpu().numpy().tobytes()).hexdigest()[:16]}
     if args.e2e and transport == "peer":
@@ -82,19 +84,19 @@ def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=Tru
 
 
 run("nccl after the kernels (round 1)", transport="nccl")
-run("nccl, redundant halo", transport="nccl", halo="redundant")
-run("peer, 1 chunk, rows-cut", chunks=1, weighted=False)
-run("peer, 1 chunk, work-cut", chunks=1)
-run("peer, 4 chunks, rows-cut", weighted=False)
+run("peer, 1 chunk, rows-cut, fused gather", chunks=1, weighted=False)
+run("peer, 1 chunk, work-cut, fused gather", chunks=1)
+run("peer, 1 chunk, work-cut, DMA gather", chunks=1, fused=0)
 run("peer, 4 chunks, work-cut (default)")
 run("peer, 4 chunks, work-cut, redundant halo", halo="redundant")
-run("peer, 3 chunks, work-cut", chunks=3)
-run("peer, 6 chunks, work-cut", chunks=6, frac=48)
-run("peer, 8 chunks, work-cut", chunks=8, frac=64)
-run("peer, 4 chunks, overlap on", overlap=True)
-run("peer, graded chunks .45/.45/.07/.03, overlap on", overlap=True, chunks=(0.45, 0.45, 0.07, 0.03))
-run("peer, graded chunks .45/.45/.07/.03, overlap on, redundant", overlap=True, halo="redundant",
-    chunks=(0.45, 0.45, 0.07, 0.03))
-run("peer, graded chunks .3/.3/.3/.07/.03, overlap on", overlap=True, chunks=(0.3, 0.3, 0.3, 0.07, 0.03))
-run("peer, graded chunks .6/.3/.1, overlap on", overlap=True, chunks=(0.6, 0.3, 0.1))
+run("peer, 2 chunks 7/8 + 1/8, work-cut", chunks=(0.875, 0.125))
+run("peer, 2 chunks 7/8 + 1/8, work-cut, redundant", chunks=(0.875, 0.125), halo="redundant")
+run("peer, 4 chunks, overlap, fused 2", overlap=True, fused=2)
+run("peer, 4 chunks, overlap, fused 2, redundant", overlap=True, fused=2, halo="redundant")
+run("peer, 4 chunks, overlap, fused 1, redundant", overlap=True, fused=1, halo="redundant")
+run("peer, graded .45/.45/.1, overlap, fused 1, redundant", overlap=True, fused=1, halo="redundant",
+    chunks=(0.45, 0.45, 0.1))
+run("peer, 3 chunks, overlap, fused 2, redundant", overlap=True, fused=2, halo="redundant", chunks=3)
+run("peer, 2 chunks 7/8 + 1/8, overlap, fused 2, redundant", overlap=True, fused=2, halo="redundant",
+    chunks=(0.875, 0.125))
 dist.destroy_process_group()
