@@ -234,8 +234,10 @@ class FTLE(LagrangianDiagnostic2D):
             with torch.cuda.device(m.device):
                 main = torch.cuda.current_stream(m.device)
                 main.wait_stream(eng.copy_stream)  # pushes of earlier calls out of reused buffers
-                steps, tail = member_schedule(s, ydim, edge_order, exchange, self.pipeline_chunks,
-                                              self.pipeline_last_fraction)
+                steps, tail = member_schedule(
+                    s, ydim, edge_order, exchange,
+                    self.device_chunks if target == "device" else self.pipeline_chunks,
+                    self.pipeline_last_fraction)
                 fm = fm_sym.view(m, torch.float64, (max(s.nloc, 1), xdim, 2))
                 if target == "device":
                     out = field_sym.view(m, torch.float64, (ydim, xdim))  # global row index
@@ -248,6 +250,19 @@ class FTLE(LagrangianDiagnostic2D):
             runs.append(dict(m=m, s=s, steps=steps, tail=tail, fm=fm, out=out, out_row0=out_row0,
                              counters=counters, main=main, pushes=0))
 
+        trace = self.trace if isinstance(self.trace, list) else None
+
+        def mark(run, label, stream):
+            """Debug timeline (``FTLE.trace = []``): a timed CUDA event on ``stream``."""
+            if trace is not None:
+                with torch.cuda.device(run["m"].device):
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record(stream)
+                trace.append((run["m"].rank, label, ev))
+
+        for run in runs:
+            mark(run, "start", run["main"])
+
         def ship(run, a, b, last, after=None):
             """FTLE rows [a, b) of this member were just enqueued on stream ``after`` (default:
             its main stream): send them on their way on the copy stream."""
@@ -257,16 +272,17 @@ class FTLE(LagrangianDiagnostic2D):
                 ev.record(after or run["main"])
                 eng.copy_stream.wait_event(ev)
                 if target == "device":
-                    run["pushes"] += 1
-                    value = gen * peer.GEN_STRIDE + (peer.DONE if last else min(run["pushes"], peer.DONE - 1))
-                    G.push_rows(m, field_sym, a * xdim * 8, (b - a) * xdim * 8, value,
+                    G.push_rows(m, field_sym, a * xdim * 8, (b - a) * xdim * 8,
+                                gen * peer.GEN_STRIDE + peer.DONE if last else None,
                                 eng.copy_stream.cuda_stream, dests)
                     run["pushed"] = torch.cuda.Event()
                     run["pushed"].record(eng.copy_stream)
+                    mark(run, f"dma-push rows {a}:{b} done", eng.copy_stream)
                 elif b > a:
                     with torch.cuda.stream(eng.copy_stream):
                         r0 = run["out_row0"]
                         host_t[a:b].copy_(run["out"][a - r0:b - r0], non_blocking=True)
+                    mark(run, f"d2h rows {a}:{b} done", eng.copy_stream)
 
         def stencil(run, g0, g1, a, b):
             """K2: FTLE rows [a, b) from the member's flow-map rows [g0, g1) (global indices)."""
@@ -284,11 +300,13 @@ class FTLE(LagrangianDiagnostic2D):
             if not (fused and target == "device"):
                 with torch.cuda.device(m.device), torch.cuda.stream(stream):
                     stencil(run, g0, g1, a, b)
+                mark(run, f"K2 rows {a}:{b} done", stream)
                 ship(run, a, b, last, stream)
                 return
-            run["pushes"] += 1
-            value = gen * peer.GEN_STRIDE + (peer.DONE if last else min(run["pushes"], peer.DONE - 1))
             peers, flags = G.push_targets(m, field_sym, a * xdim * 8, dests)
+            value = gen * peer.GEN_STRIDE + peer.DONE
+            if not last:
+                flags = []
             lo = run["s"].lo
             with torch.cuda.device(m.device), torch.cuda.stream(stream):
                 if run.get("pushed") is not None:  # the flag must not overtake earlier DMA pushes
@@ -296,6 +314,7 @@ class FTLE(LagrangianDiagnostic2D):
                 eng.ftle_stencil_gather(run["fm"][g0 - lo:g1 - lo], g0, self._xf, self._yf,
                                         edge_order, t_span, a, b - a, run["out"][a:b], peers,
                                         flags, value)
+            mark(run, f"K2+gather rows {a}:{b} done", stream)
 
         # chunk-major over the local members, so that every device has work queued before the
         # host moves on to the next chunk
@@ -326,6 +345,7 @@ class FTLE(LagrangianDiagnostic2D):
                         ev = torch.cuda.Event()
                         ev.record(k1s)
                         run["k1_events"].append(ev)
+                mark(run, f"K1 rows {r0}:{r1} done", k1s)
                 if upto > done:
                     k2s = run["k2_stream"]
                     if overlap:
@@ -348,7 +368,9 @@ class FTLE(LagrangianDiagnostic2D):
         for run in runs:
             m, s = run["m"], run["s"]
             if run["tail"]:
+                mark(run, "halo pushed", run["main"])
                 G.halo_wait(m, slabs, gen, run["main"].cuda_stream)
+                mark(run, "halo arrived", run["main"])
                 for k, (a, b) in enumerate(run["tail"]):
                     produce(run, s.lo, s.hi, a, b, k == len(run["tail"]) - 1, True, run["main"])
             elif not s.rows:
@@ -364,6 +386,7 @@ class FTLE(LagrangianDiagnostic2D):
             for run in runs:
                 if dests is None or run["m"].rank in dests:
                     G.wait_gathered(run["m"], gen, run["main"].cuda_stream)
+                    mark(run, "all rows gathered", run["main"])
             self.field_device = first["out"]
             return first["out"]
         for run in runs:
@@ -411,10 +434,16 @@ class FTLE(LagrangianDiagnostic2D):
     # K1 chunks on alternating streams (chunk c+1 fills the SMs as chunk c drains), K2 on its own
     # high-priority stream; False: everything in order on one stream (K2 between the chunks)
     overlap_chunks = False
+    trace = None  # set to [] to collect (rank, label, timed CUDA event) of the next group call
     # device result: the K2 launches of this many last chunks (and of the rows that wait for a
     # halo exchange) store straight into the other GPUs' fields (dlb_ftle_stencil_gather);
     # earlier chunks are pushed by a copy engine behind the integrator
     fused_gather_chunks = 1
+    # device result on several GPUs: chunk sizes (fractions of a slab's rows).  One large chunk
+    # whose rows a copy engine spreads while the small last one integrates; the last one's K2 is
+    # the fused gather.  (The host result keeps `pipeline_chunks`: equal chunks, because there
+    # the box-wide device-to-host bandwidth is the limit.)
+    device_chunks = (0.9, 0.1)
 
     def _gather_flow_map(self, G, fm_sym, slabs, m):
         """The reference's `flow_map` attribute (R:_base_classes.py:187): collected on demand by

@@ -147,11 +147,15 @@ class Group:
         n = self.size
         on = set(range(n) if dests is None else dests)
         dst = (C.c_void_p * n)(*[row[j] + byte_offset if j in on else None for j in range(n)])
-        flg = (C.c_void_p * n)(*[frow[j] + 8 * m.rank if j in on else None for j in range(n)])
+        # flag_value None: copies only (an earlier chunk; only the member's last departure
+        # raises the flags, and the signal kernel needs an SM slot the integrator may not free
+        # before its chunk ends)
+        flg = (C.c_void_p * n)(*[frow[j] + 8 * m.rank if (j in on and flag_value is not None)
+                                 else None for j in range(n)])
         with torch.cuda.device(m.device):
             nat.check(nat.lib.dlb_gather_rows(row[m.rank] + byte_offset, int(nbytes), dst, n, flg,
-                                              int(flag_value), stream))
-        m.engine.launches += 1
+                                              int(flag_value or 0), stream))
+        m.engine.launches += int(flag_value is not None)
 
     def push_targets(self, m: Member, buf: SymBuf, byte_offset: int, dests=None):
         """(peer addresses, flag addresses) for ``dlb_ftle_stencil_gather``: where member m's rows

@@ -18,6 +18,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--e2e", action="store_true", help="also time FTLE().compute (host field)")
+ap.add_argument("--trace", action="store_true", help="print an event timeline of one step")
+ap.add_argument("--only", default="", help="substring filter on variant names")
 args = ap.parse_args()
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 local = int(os.environ["LOCAL_RANK"])
@@ -35,11 +37,14 @@ eng = Engine.get()
 
 
 def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=True, overlap=None,
-        fused=1):
+        fused=1, hchunks=4):
+    if args.only and args.only not in name:
+        return
     sharding.set_transport(transport)
     sharding.set_halo_mode(halo)
     d = FTLE()
-    d.pipeline_chunks, d.pipeline_last_fraction, d.weighted_slabs = chunks, frac, weighted
+    d.pipeline_chunks, d.pipeline_last_fraction, d.weighted_slabs = hchunks, frac, weighted
+    d.device_chunks = chunks
     if overlap is not None:
         d.overlap_chunks = overlap
     d.fused_gather_chunks = fused
@@ -67,6 +72,24 @@ def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=Tru
            "weighted": weighted, "overlap": overlap, "fused": fused, "ms_per_step": float(tmax[0]),
            "k1_ms_max_rank": float(tmax[1]), "k1_ms_min_rank": float(tmin[1]),
            "sha": hashlib.sha256(f.cpu().numpy().tobytes()).hexdigest()[:16]}
+    if args.trace and transport == "peer":
+        dist.barrier()
+        torch.cuda.synchronize()
+        d.trace = []
+        d.compute_device(x, y, double_gyre, (10, 0), **kw)
+        torch.cuda.synchronize()
+        tr, d.trace = d.trace, None
+        t0 = tr[0][2]
+        out["timeline_ms_rank%d" % rank] = [[lab, round(t0.elapsed_time(ev), 3)] for _, lab, ev in tr]
+        if rank not in (0, world - 1, world // 2):
+            out.pop("timeline_ms_rank%d" % rank)
+        ends = torch.tensor([t0.elapsed_time(tr[-1][2])], dtype=torch.float64, device="cuda")
+        allends = [torch.zeros_like(ends) for _ in range(world)]
+        dist.all_gather(allends, ends)
+        out["end_ms_by_rank"] = [round(float(e[0]), 3) for e in allends]
+        if rank in (world - 1, world // 2) and rank != 0:
+            print(json.dumps({"variant": name, "rank": rank,
+                              "timeline": out.pop("timeline_ms_rank%d" % rank)}), flush=True)
     if args.e2e and transport == "peer":
         import time
         for _ in range(3):
@@ -84,19 +107,18 @@ def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=Tru
 
 
 run("nccl after the kernels (round 1)", transport="nccl")
-run("peer, 1 chunk, rows-cut, fused gather", chunks=1, weighted=False)
-run("peer, 1 chunk, work-cut, fused gather", chunks=1)
-run("peer, 1 chunk, work-cut, DMA gather", chunks=1, fused=0)
-run("peer, 4 chunks, work-cut (default)")
-run("peer, 4 chunks, work-cut, redundant halo", halo="redundant")
-run("peer, 2 chunks 7/8 + 1/8, work-cut", chunks=(0.875, 0.125))
-run("peer, 2 chunks 7/8 + 1/8, work-cut, redundant", chunks=(0.875, 0.125), halo="redundant")
-run("peer, 4 chunks, overlap, fused 2", overlap=True, fused=2)
-run("peer, 4 chunks, overlap, fused 2, redundant", overlap=True, fused=2, halo="redundant")
-run("peer, 4 chunks, overlap, fused 1, redundant", overlap=True, fused=1, halo="redundant")
-run("peer, graded .45/.45/.1, overlap, fused 1, redundant", overlap=True, fused=1, halo="redundant",
-    chunks=(0.45, 0.45, 0.1))
-run("peer, 3 chunks, overlap, fused 2, redundant", overlap=True, fused=2, halo="redundant", chunks=3)
-run("peer, 2 chunks 7/8 + 1/8, overlap, fused 2, redundant", overlap=True, fused=2, halo="redundant",
-    chunks=(0.875, 0.125))
+run("peer, 2 chunks .875/.125", chunks=(0.875, 0.125))
+run("peer, 2 chunks .875/.125, redundant", chunks=(0.875, 0.125), halo="redundant")
+run("peer, 2 chunks .9/.1, redundant", chunks=(0.9, 0.1), halo="redundant")
+run("peer, 2 chunks .9375/.0625, redundant", chunks=(0.9375, 0.0625), halo="redundant")
+run("peer, 3 chunks .5/.4/.1, redundant", chunks=(0.5, 0.4, 0.1), halo="redundant")
+run("peer, 2 chunks .875/.125, redundant, DMA only", chunks=(0.875, 0.125), halo="redundant", fused=0)
+run("peer, 2 chunks .875/.125, overlap, redundant", chunks=(0.875, 0.125), halo="redundant", overlap=True)
+run("peer, 4 chunks, overlap, fused 1, redundant", overlap=True, fused=1, halo="redundant", chunks=4)
+run("peer, 3 chunks .6/.3/.1, overlap, fused 1, redundant", overlap=True, fused=1, halo="redundant",
+    chunks=(0.6, 0.3, 0.1))
+run("host chunks 4", hchunks=4, halo="redundant")
+run("host chunks 5", hchunks=5, halo="redundant")
+run("host chunks 6/48", hchunks=6, frac=48, halo="redundant")
+run("host chunks 4, overlap", hchunks=4, halo="redundant", overlap=True)
 dist.destroy_process_group()
