@@ -107,13 +107,14 @@ class Engine:
         the chunk's y rows on every K1 launch; from pageable memory that cudaMemcpyAsync first
         waits for the stream to drain, from pinned memory it is a plain enqueue."""
         key = a.tobytes()
-        hit = self._pinned.get(key)
+        hit = self._pinned.pop(key, None)
         if hit is None:
-            if len(self._pinned) >= 16:
-                self._pinned.clear()
+            if len(self._pinned) >= 64:  # drop the least recently used (long idle by then)
+                self._pinned.pop(next(iter(self._pinned)))
             t = torch.empty(max(a.size, 1), dtype=_F64, pin_memory=True)
             t[:a.size].copy_(torch.from_numpy(a))
-            hit = self._pinned[key] = (t, t.numpy()[:a.size])
+            hit = (t, t.numpy()[:a.size])
+        self._pinned[key] = hit  # most recently used last
         return hit[1]
 
     def empty(self, *shape, dtype=_F64):
@@ -276,7 +277,9 @@ class Engine:
                 ws, wsz = self.workspace(xdim, max(len(y), rows))
             else:
                 ws, wsz = self.k1_workspace(ws_slot, xdim, rows)
-                x, y = self.pinned_coord(x), self.pinned_coord(y)
+            # the library uploads x and y[row0:row0+rows] on every launch: from page-locked copies
+            # that is a plain enqueue, from pageable memory the call would first drain the stream
+            x, y = self.pinned_coord(x), self.pinned_coord(y)
             p = nat.darray(params)
             with self._timed("rk45_flowmap"):
               nat.check(nat.lib.dlb_flowmap_rk45(
