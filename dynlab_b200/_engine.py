@@ -56,7 +56,7 @@ class Engine:
         self.alt_stream = torch.cuda.Stream(device=self.device)
         self.stencil_stream = torch.cuda.Stream(device=self.device, priority=-1)
         self._k1_ws = {}      # slot -> private K1 workspace (work counter + x, y rows)
-        self._pinned = {}     # coordinate bytes -> pinned host copy
+        self._coords = {}     # coordinate bytes -> device-resident copy
         self.profile = None  # set to {} to collect (start, end) CUDA events per kernel name
         self.launches = 0    # kernels of libdynlab_b200.so launched through this engine
 
@@ -102,20 +102,18 @@ class Engine:
                                                  device=self.device)
         return ws.data_ptr(), ws.numel()
 
-    def pinned_coord(self, a: np.ndarray) -> np.ndarray:
-        """Page-locked copy of a coordinate vector (cached by value).  The library uploads x and
-        the chunk's y rows on every K1 launch; from pageable memory that cudaMemcpyAsync first
-        waits for the stream to drain, from pinned memory it is a plain enqueue."""
+    def device_coord(self, a: np.ndarray) -> torch.Tensor:
+        """Device-resident copy of a coordinate vector, cached by value: K1 launches read x and
+        y from it (``dlb_flowmap_rk45_resident``) instead of uploading them every time."""
         key = a.tobytes()
-        hit = self._pinned.pop(key, None)
+        hit = self._coords.pop(key, None)
         if hit is None:
-            if len(self._pinned) >= 64:  # drop the least recently used (long idle by then)
-                self._pinned.pop(next(iter(self._pinned)))
-            t = torch.empty(max(a.size, 1), dtype=_F64, pin_memory=True)
-            t[:a.size].copy_(torch.from_numpy(a))
-            hit = (t, t.numpy()[:a.size])
-        self._pinned[key] = hit  # most recently used last
-        return hit[1]
+            if len(self._coords) >= 64:  # drop the least recently used (long idle by then)
+                self._coords.pop(next(iter(self._coords)))
+            with torch.cuda.device(self.device):
+                hit = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+        self._coords[key] = hit  # most recently used last
+        return hit
 
     def empty(self, *shape, dtype=_F64):
         return torch.empty(*shape, dtype=dtype, device=self.device)
@@ -277,13 +275,11 @@ class Engine:
                 ws, wsz = self.workspace(xdim, max(len(y), rows))
             else:
                 ws, wsz = self.k1_workspace(ws_slot, xdim, rows)
-            # the library uploads x and y[row0:row0+rows] on every launch: from page-locked copies
-            # that is a plain enqueue, from pageable memory the call would first drain the stream
-            x, y = self.pinned_coord(x), self.pinned_coord(y)
             p = nat.darray(params)
+            dx, dy = self.device_coord(x), self.device_coord(y)
             with self._timed("rk45_flowmap"):
-              nat.check(nat.lib.dlb_flowmap_rk45(
-                flow_id, p, len(params), nat.dptr(x), xdim, nat.dptr(y), row0, rows,
+              nat.check(nat.lib.dlb_flowmap_rk45_resident(
+                flow_id, p, len(params), dx.data_ptr(), xdim, dy.data_ptr(), row0, rows,
                 float(t0), float(tf), float(rtol), float(atol), float(max_step), float(first_step),
                 out.data_ptr(), nfev.data_ptr() if nfev is not None else None,
                 status.data_ptr() if status is not None else None,

@@ -491,47 +491,24 @@ extern "C" size_t dlb_workspace_bytes(int64_t xdim, int64_t ydim) {
   return 256 + sizeof(double) * (size_t)(5 * (xdim + ydim) + 4 * ydim + 64);
 }
 
-extern "C" int dlb_flowmap_rk45(int flow_id, const double* h_params, int n_params,
-                                const double* h_x, int64_t xdim, const double* h_y, int64_t row0,
-                                int64_t rows, double t0, double tf, double rtol, double atol,
-                                double max_step, double first_step, double* d_flow_map,
-                                uint32_t* d_nfev, int8_t* d_status, uint64_t* d_counters,
-                                void* d_workspace, size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  if (!h_x || !h_y || !d_flow_map || !d_counters || !d_workspace || xdim < 1 || rows < 0 ||
-      row0 < 0) {
-    dlb_set_error("dlb_flowmap_rk45: bad argument");
-    return DLB_ERR_ARG;
-  }
-  if (flow_id < 0 || flow_id >= DLB_FLOW_COUNT || k_flow_info[flow_id].dim != 2) {
-    dlb_set_error("dlb_flowmap_rk45: flow %d is not a 2-D flow", flow_id);
-    return DLB_ERR_ARG;
-  }
-  if (!(atol >= 0)) {  // common.py:57-58
-    dlb_set_error("`atol` must be positive.");
-    return DLB_ERR_ARG;
-  }
-  if (workspace_bytes < dlb_workspace_bytes(xdim, rows)) {
-    dlb_set_error("workspace too small");
-    return DLB_ERR_WORKSPACE;
-  }
+namespace {
+// K1 over a row slab with the coordinates already on the device: d_x[xdim], d_yrows[rows].
+int flowmap_launch(int flow_id, const double* h_params, int n_params, const double* d_x,
+                   int64_t xdim, const double* d_yrows, int64_t rows, double t0, double tf,
+                   double rtol, double atol, double max_step, double first_step,
+                   double* d_flow_map, uint32_t* d_nfev, int8_t* d_status, uint64_t* d_counters,
+                   void* d_workspace, cudaStream_t stream) {
   Rk45Params P;
   memset(&P, 0, sizeof(P));
   int rc = fill_common(P, flow_id, h_params, n_params, t0, tf, rtol, max_step, first_step);
   if (rc) return rc;
   P.atol[0] = P.atol[1] = P.atol[2] = atol;
   char* ws = (char*)d_workspace;
-  double* d_x = (double*)(ws + 256);
-  double* d_y = d_x + xdim;
-  dlb_axes_cache_note_layout(d_workspace, xdim, rows);
   DLB_CUDA_CHECK(cudaMemsetAsync(ws, 0, 256, stream));
   DLB_CUDA_CHECK(cudaMemsetAsync(d_counters, 0, sizeof(uint64_t) * DLB_CNT_WORDS, stream));
   if (rows == 0) return DLB_OK;
-  DLB_CUDA_CHECK(cudaMemcpyAsync(d_x, h_x, sizeof(double) * xdim, cudaMemcpyHostToDevice, stream));
-  DLB_CUDA_CHECK(
-      cudaMemcpyAsync(d_y, h_y + row0, sizeof(double) * rows, cudaMemcpyHostToDevice, stream));
   P.x = d_x;
-  P.y = d_y;
+  P.y = d_yrows;
   P.xdim = xdim;
   P.total = (long long)xdim * rows;
   P.out = d_flow_map;
@@ -544,6 +521,73 @@ extern "C" int dlb_flowmap_rk45(int flow_id, const double* h_params, int n_param
     if constexpr (ID < DLB_FLOW_ABC) rc = launch_rk45<ID, 2, true>(P, stream);
   });
   return rc;
+}
+
+int flowmap_check(const char* who, int flow_id, const void* x, const void* y, const void* out,
+                  const void* counters, const void* ws, int64_t xdim, int64_t rows, int64_t row0,
+                  double atol) {
+  if (!x || !y || !out || !counters || !ws || xdim < 1 || rows < 0 || row0 < 0) {
+    dlb_set_error("%s: bad argument", who);
+    return DLB_ERR_ARG;
+  }
+  if (flow_id < 0 || flow_id >= DLB_FLOW_COUNT || k_flow_info[flow_id].dim != 2) {
+    dlb_set_error("%s: flow %d is not a 2-D flow", who, flow_id);
+    return DLB_ERR_ARG;
+  }
+  if (!(atol >= 0)) {  // common.py:57-58
+    dlb_set_error("`atol` must be positive.");
+    return DLB_ERR_ARG;
+  }
+  return DLB_OK;
+}
+}  // namespace
+
+extern "C" int dlb_flowmap_rk45(int flow_id, const double* h_params, int n_params,
+                                const double* h_x, int64_t xdim, const double* h_y, int64_t row0,
+                                int64_t rows, double t0, double tf, double rtol, double atol,
+                                double max_step, double first_step, double* d_flow_map,
+                                uint32_t* d_nfev, int8_t* d_status, uint64_t* d_counters,
+                                void* d_workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = flowmap_check("dlb_flowmap_rk45", flow_id, h_x, h_y, d_flow_map, d_counters,
+                         d_workspace, xdim, rows, row0, atol);
+  if (rc) return rc;
+  if (workspace_bytes < dlb_workspace_bytes(xdim, rows)) {
+    dlb_set_error("workspace too small");
+    return DLB_ERR_WORKSPACE;
+  }
+  char* ws = (char*)d_workspace;
+  double* d_x = (double*)(ws + 256);
+  double* d_y = d_x + xdim;
+  dlb_axes_cache_note_layout(d_workspace, xdim, rows);
+  if (rows > 0) {
+    DLB_CUDA_CHECK(
+        cudaMemcpyAsync(d_x, h_x, sizeof(double) * xdim, cudaMemcpyHostToDevice, stream));
+    DLB_CUDA_CHECK(
+        cudaMemcpyAsync(d_y, h_y + row0, sizeof(double) * rows, cudaMemcpyHostToDevice, stream));
+  }
+  return flowmap_launch(flow_id, h_params, n_params, d_x, xdim, d_y, rows, t0, tf, rtol, atol,
+                        max_step, first_step, d_flow_map, d_nfev, d_status, d_counters,
+                        d_workspace, stream);
+}
+
+extern "C" int dlb_flowmap_rk45_resident(int flow_id, const double* h_params, int n_params,
+                                         const double* d_x, int64_t xdim, const double* d_y,
+                                         int64_t row0, int64_t rows, double t0, double tf,
+                                         double rtol, double atol, double max_step,
+                                         double first_step, double* d_flow_map, uint32_t* d_nfev,
+                                         int8_t* d_status, uint64_t* d_counters,
+                                         void* d_workspace, size_t workspace_bytes, void* stream_) {
+  int rc = flowmap_check("dlb_flowmap_rk45_resident", flow_id, d_x, d_y, d_flow_map, d_counters,
+                         d_workspace, xdim, rows, row0, atol);
+  if (rc) return rc;
+  if (workspace_bytes < 256) {
+    dlb_set_error("workspace too small");
+    return DLB_ERR_WORKSPACE;
+  }
+  return flowmap_launch(flow_id, h_params, n_params, d_x, xdim, d_y + row0, rows, t0, tf, rtol,
+                        atol, max_step, first_step, d_flow_map, d_nfev, d_status, d_counters,
+                        d_workspace, (cudaStream_t)stream_);
 }
 
 extern "C" int dlb_rk45_endpoints(int flow_id, const double* h_params, int n_params, int n_dim,

@@ -127,6 +127,18 @@ int dlb_flowmap_rk45(int flow_id, const double* h_params, int n_params,
                      uint64_t* d_counters, void* d_workspace, size_t workspace_bytes,
                      void* stream);
 
+/* Same kernel with the coordinate vectors already resident on the device (d_x[xdim], d_y[at
+ * least row0+rows]): nothing is uploaded, so a launch is two 64-byte memsets and the kernel.
+ * Chunked / multi-GPU pipelines call this once per row chunk; an upload per launch would queue
+ * behind the peer copies on the copy engines.  The workspace only holds the 256-byte work
+ * counter here. */
+int dlb_flowmap_rk45_resident(int flow_id, const double* h_params, int n_params,
+                              const double* d_x, int64_t xdim, const double* d_y, int64_t row0,
+                              int64_t rows, double t0, double tf, double rtol, double atol,
+                              double max_step, double first_step, double* d_flow_map,
+                              uint32_t* d_nfev, int8_t* d_status, uint64_t* d_counters,
+                              void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* K1 (generic) — endpoints of m seeds of dimension n_dim (2 or 3; must match the flow).
  * d_seeds/d_out: [m][n_dim].  h_atol: n_dim values.  Same semantics as above; this is the
  * entry the integrator-protocol wrapper `integrator(f, t, Y0)[-1, :]` maps to
