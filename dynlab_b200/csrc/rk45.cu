@@ -556,6 +556,12 @@ extern "C" int dlb_flowmap_rk45(int flow_id, const double* h_params, int n_param
     dlb_set_error("workspace too small");
     return DLB_ERR_WORKSPACE;
   }
+  {  // argument validation happens before any CUDA call
+    Rk45Params probe;
+    memset(&probe, 0, sizeof(probe));
+    rc = fill_common(probe, flow_id, h_params, n_params, t0, tf, rtol, max_step, first_step);
+    if (rc) return rc;
+  }
   char* ws = (char*)d_workspace;
   double* d_x = (double*)(ws + 256);
   double* d_y = d_x + xdim;
