@@ -443,7 +443,7 @@ class FTLE(LagrangianDiagnostic2D):
     # whose rows a copy engine spreads while the small last one integrates; the last one's K2 is
     # the fused gather.  (The host result keeps `pipeline_chunks`: equal chunks, because there
     # the box-wide device-to-host bandwidth is the limit.)
-    device_chunks = (0.9, 0.1)
+    device_chunks = (0.875, 0.125)
 
     def _gather_flow_map(self, G, fm_sym, slabs, m):
         """The reference's `flow_map` attribute (R:_base_classes.py:187): collected on demand by

@@ -1037,6 +1037,6 @@ def test_single_process_group_matches_single_device(dl):
             peer.current_group(nx * ny).check_timeouts()
     finally:
         peer.set_devices("auto")
-        sharding.set_halo_mode("exchange")
+        sharding.set_halo_mode("redundant")
 
 

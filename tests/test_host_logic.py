@@ -308,10 +308,10 @@ def test_shared_host_segment_gloo(tmp_path, size):
 def test_sharding_mode_switches_validate():
     from dynlab_b200 import sharding
 
-    assert sharding.halo_mode() == "exchange"
-    sharding.set_halo_mode("redundant")
     assert sharding.halo_mode() == "redundant"
     sharding.set_halo_mode("exchange")
+    assert sharding.halo_mode() == "exchange"
+    sharding.set_halo_mode("redundant")
     with pytest.raises(ValueError):
         sharding.set_halo_mode("both")
     with pytest.raises(ValueError):

@@ -94,7 +94,7 @@ for (nx, ny, eo, t) in grids:
                     torch.cuda.synchronize()
                     results[f"{tag}/device{rep}"] = np.array_equal(fd.cpu().numpy(), f_1)
     sharding.set_transport("peer")
-    sharding.set_halo_mode("exchange")
+    sharding.set_halo_mode("redundant")
     g = peer.current_group(nx * ny)
     g.check_timeouts()
     # ---- LCS / Eulerian (NCCL gather path; needs distinct devices)
