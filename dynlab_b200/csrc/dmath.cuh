@@ -33,7 +33,7 @@ namespace dm {
 //   [4] 1.5 * 2^52 (rint magic)
 //   [5..10]  k_sin minimax coefficients S6..S1 on [-pi/4, pi/4] (fdlibm set)
 //   [11..16] k_cos minimax coefficients C6..C1
-__constant__ double DM_K[18] = {
+__constant__ double DM_K[20] = {
     0x1.45f306dc9c883p-1,          // 2/pi
     0x1.921fb54442d18p+0,          // P1
     0x1.1a62633145c07p-54,         // P2
@@ -51,6 +51,8 @@ __constant__ double DM_K[18] = {
     2.48015872894767294178e-05,    // C3
     -1.38888888888741095749e-03,   // C2
     4.16666666666666019037e-02,    // C1
+    0.0,
+    3.141592653589793,             // [18] np.pi (reduction in units of pi, sincospi2)
     0.0,
 };
 // Constant provider: reads the table through the constant cache (LDCU into uniform registers).
@@ -210,6 +212,44 @@ struct TrigFast {
     *s1 = fix_sin(sn1, cs1, q1);
     *c1 = fix_cos(sn1, cs1, q1);
   }
+  // sin / cos of pi*a0 and pi*a1 (the double gyre's sin(pi f), cos(pi y)).  The reference forms
+  // fl(pi*a) and takes sin / cos of that; here the argument is reduced in units of pi FIRST:
+  // q = rint(2a), a - q/2 is exact, r = pi (a - q/2) is rounded once - one multiply instead of
+  // pi*a plus the three-term Cody-Waite subtraction (4 FP64 instructions instead of 6 per
+  // argument, 24 per RK attempt).  Differs from sin(fl(pi a)) by the rounding of pi*a, i.e. by
+  // <= ulp(pi a) / 2 absolute (exactly 0 / +-1 where a is a multiple of 1/2).  Only the
+  // integrator's attempt loop uses it; the start-up RHS (scipy's `d1 <= 1e-15` test on the
+  // walls x = 2, y = 1 sees the reference's 1.2e-16) goes through TrigSafe.
+  __device__ __forceinline__ void sincospi2(double a0, double a1, double* s0, double* c0,
+                                            double* s1, double* c1) {
+#ifdef DLB_NO_PI_UNIT
+    sincos2(K_PI() * a0, a1 * K_PI(), s0, c0, s1, c1);
+#else
+    const KC K;
+    big = max(big, max(hi_abs(a0), hi_abs(a1)));
+    const double t0 = fma(a0, 2.0, DM_MAGIC), t1 = fma(a1, 2.0, DM_MAGIC);
+    const int q0 = __double2loint(t0), q1 = __double2loint(t1);
+    const double r0 = fma(t0 - DM_MAGIC, -0.5, a0) * K[18];
+    const double r1 = fma(t1 - DM_MAGIC, -0.5, a1) * K[18];
+    const double z0 = r0 * r0, z1 = r1 * r1;
+    double ps0 = fma(DM_S(6), z0, DM_S(5)), ps1 = fma(DM_S(6), z1, DM_S(5));
+    double pc0 = fma(DM_C(6), z0, DM_C(5)), pc1 = fma(DM_C(6), z1, DM_C(5));
+#pragma unroll
+    for (int k = 4; k >= 1; --k) {
+      ps0 = fma(ps0, z0, DM_S(k));
+      ps1 = fma(ps1, z1, DM_S(k));
+      pc0 = fma(pc0, z0, DM_C(k));
+      pc1 = fma(pc1, z1, DM_C(k));
+    }
+    const double sn0 = fma(r0 * z0, ps0, r0), sn1 = fma(r1 * z1, ps1, r1);
+    const double cs0 = fma(z0, fma(z0, pc0, -0.5), 1.0), cs1 = fma(z1, fma(z1, pc1, -0.5), 1.0);
+    *s0 = fix_sin(sn0, cs0, q0);
+    *c0 = fix_cos(sn0, cs0, q0);
+    *s1 = fix_sin(sn1, cs1, q1);
+    *c1 = fix_cos(sn1, cs1, q1);
+#endif
+  }
+  static __device__ __forceinline__ double K_PI() { return DM_K[18]; }
   // NS independent sines (COS: cosines), chains interleaved; out has stride `stride` doubles
   template <int NS, bool COS>
   __device__ __forceinline__ void sinN(const double* arg, double* out, int stride) {
@@ -253,6 +293,12 @@ struct TrigSafe {
                                           double* s1, double* c1) {
     dm::sincos(a0, s0, c0);
     dm::sincos(a1, s1, c1);
+  }
+  // sin / cos of pi*a0, pi*a1 exactly as the reference forms them: fl(pi * a) first
+  __device__ __forceinline__ void sincospi2(double a0, double a1, double* s0, double* c0,
+                                            double* s1, double* c1) {
+    dm::sincos(3.141592653589793 * a0, s0, c0);
+    dm::sincos(a1 * 3.141592653589793, s1, c1);
   }
   template <int NS, bool COS>
   __device__ __forceinline__ void sinN(const double* arg, double* out, int stride) {

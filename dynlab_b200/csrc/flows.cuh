@@ -234,7 +234,7 @@ __device__ __forceinline__ void flow_space(const FlowConsts& fc, Trig& trig, con
     const double f = x * fma(a, x, b);       // a x^2 + b x
     const double dfdx = fma(2 * a, x, b);    // 2 a x + b
     double sf, cf, sy, cy;
-    trig.sincos2(DLB_PI * f, y * DLB_PI, &sf, &cf, &sy, &cy);
+    trig.sincospi2(f, y, &sf, &cf, &sy, &cy);  // sin / cos of pi f and of y pi
     out[0] = c[3] * sf * cy;
     out[1] = c[4] * cf * sy * dfdx;
   } else if constexpr (ID == DLB_FLOW_AUTONOMOUS_DOUBLE_GYRE) {
