@@ -91,6 +91,22 @@ __device__ __forceinline__ double reduce_pio2(const KT& K, double x, int* q) {
   return r;
 }
 
+// The same with pi/2 = P1 + P2 only (106 bits): the dropped term is |q| * 1.2e-33, below half an
+// ulp of r unless |r| < |q| * 1e-17 - for the bounded arguments of an integration (|q| < 100)
+// that is the exact lattice x = q pi/2 itself, where it changes r by 2e-17 relative.  One FP64
+// instruction less per argument; used by TrigFast (the integrator's attempt loop) only.
+template <class KT>
+__device__ __forceinline__ double reduce_pio2_fast(const KT& K, double x, int* q) {
+#ifdef DLB_TRIG_3TERM
+  return reduce_pio2(K, x, q);
+#else
+  const double t = fma(x, DM_2_OVER_PI, DM_MAGIC);
+  *q = __double2loint(t);
+  const double fq = t - DM_MAGIC;
+  return fma(-fq, DM_PIO2_2, fma(-fq, DM_PIO2_1, x));
+#endif
+}
+
 template <class KT>
 __device__ __forceinline__ double k_sin(const KT& K, double r, double r2) {
   double p = fma(DM_S(6), r2, DM_S(5));
@@ -194,7 +210,7 @@ struct TrigFast {
     const KC K;
     big = max(big, max(hi_abs(a0), hi_abs(a1)));
     int q0, q1;
-    const double r0 = reduce_pio2(K, a0, &q0), r1 = reduce_pio2(K, a1, &q1);
+    const double r0 = reduce_pio2_fast(K, a0, &q0), r1 = reduce_pio2_fast(K, a1, &q1);
     const double z0 = r0 * r0, z1 = r1 * r1;
     double ps0 = fma(DM_S(6), z0, DM_S(5)), ps1 = fma(DM_S(6), z1, DM_S(5));
     double pc0 = fma(DM_C(6), z0, DM_C(5)), pc1 = fma(DM_C(6), z1, DM_C(5));
@@ -212,44 +228,16 @@ struct TrigFast {
     *s1 = fix_sin(sn1, cs1, q1);
     *c1 = fix_cos(sn1, cs1, q1);
   }
-  // sin / cos of pi*a0 and pi*a1 (the double gyre's sin(pi f), cos(pi y)).  The reference forms
-  // fl(pi*a) and takes sin / cos of that; here the argument is reduced in units of pi FIRST:
-  // q = rint(2a), a - q/2 is exact, r = pi (a - q/2) is rounded once - one multiply instead of
-  // pi*a plus the three-term Cody-Waite subtraction (4 FP64 instructions instead of 6 per
-  // argument, 24 per RK attempt).  Differs from sin(fl(pi a)) by the rounding of pi*a, i.e. by
-  // <= ulp(pi a) / 2 absolute (exactly 0 / +-1 where a is a multiple of 1/2).  Only the
-  // integrator's attempt loop uses it; the start-up RHS (scipy's `d1 <= 1e-15` test on the
-  // walls x = 2, y = 1 sees the reference's 1.2e-16) goes through TrigSafe.
+  // sin / cos of pi*a0 and of a1*pi (the double gyre's sin(pi f), cos(pi y)), formed like the
+  // reference: fl(pi * a) first.  (Reducing a itself in units of pi - q = rint(2a), r = pi (a -
+  // q/2), 4 FP64 instructions instead of 5 - was measured 3.7 % faster on K1 and is NOT used: it
+  // makes sin(pi * 1.0) exactly 0 where the reference has sin(fl(pi)) = 1.2e-16, and the
+  // reference's eigenvector signs on the invariant wall y = 1 are decided by that residue:
+  // test_lcs_fields_against_reference failed.)
   __device__ __forceinline__ void sincospi2(double a0, double a1, double* s0, double* c0,
                                             double* s1, double* c1) {
-#ifdef DLB_NO_PI_UNIT
-    sincos2(K_PI() * a0, a1 * K_PI(), s0, c0, s1, c1);
-#else
-    const KC K;
-    big = max(big, max(hi_abs(a0), hi_abs(a1)));
-    const double t0 = fma(a0, 2.0, DM_MAGIC), t1 = fma(a1, 2.0, DM_MAGIC);
-    const int q0 = __double2loint(t0), q1 = __double2loint(t1);
-    const double r0 = fma(t0 - DM_MAGIC, -0.5, a0) * K[18];
-    const double r1 = fma(t1 - DM_MAGIC, -0.5, a1) * K[18];
-    const double z0 = r0 * r0, z1 = r1 * r1;
-    double ps0 = fma(DM_S(6), z0, DM_S(5)), ps1 = fma(DM_S(6), z1, DM_S(5));
-    double pc0 = fma(DM_C(6), z0, DM_C(5)), pc1 = fma(DM_C(6), z1, DM_C(5));
-#pragma unroll
-    for (int k = 4; k >= 1; --k) {
-      ps0 = fma(ps0, z0, DM_S(k));
-      ps1 = fma(ps1, z1, DM_S(k));
-      pc0 = fma(pc0, z0, DM_C(k));
-      pc1 = fma(pc1, z1, DM_C(k));
-    }
-    const double sn0 = fma(r0 * z0, ps0, r0), sn1 = fma(r1 * z1, ps1, r1);
-    const double cs0 = fma(z0, fma(z0, pc0, -0.5), 1.0), cs1 = fma(z1, fma(z1, pc1, -0.5), 1.0);
-    *s0 = fix_sin(sn0, cs0, q0);
-    *c0 = fix_cos(sn0, cs0, q0);
-    *s1 = fix_sin(sn1, cs1, q1);
-    *c1 = fix_cos(sn1, cs1, q1);
-#endif
+    sincos2(DM_K[18] * a0, a1 * DM_K[18], s0, c0, s1, c1);
   }
-  static __device__ __forceinline__ double K_PI() { return DM_K[18]; }
   // NS independent sines (COS: cosines), chains interleaved; out has stride `stride` doubles
   template <int NS, bool COS>
   __device__ __forceinline__ void sinN(const double* arg, double* out, int stride) {
@@ -259,7 +247,7 @@ struct TrigFast {
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
       big = max(big, hi_abs(arg[s]));
-      r[s] = reduce_pio2(K, arg[s], &q[s]);
+      r[s] = reduce_pio2_fast(K, arg[s], &q[s]);
     }
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
