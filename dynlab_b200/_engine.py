@@ -471,21 +471,24 @@ class Engine:
                 n_host = torch.empty(1, dtype=torch.int64, pin_memory=True)
                 h["count"].record_stream(cs)
                 n_host.copy_(h["count"], non_blocking=True)
-                cs.synchronize()
-                n = int(n_host[0])
-                if n > h["cap"]:  # did not fit: run again with room (on the main stream)
-                    Engine._contour_cap = n + n // 4
-                    return self.contour_fetch(self.contour_launch(
-                        h["z"], h["mask"], h["x"], h["y"], h["level"], cap=n + n // 8))
-                Engine._contour_cap = max(Engine._contour_cap, n + n // 4)
-                out = []
+            cs.synchronize()
+            n = int(n_host[0])
+            if n > h["cap"]:
+                # did not fit: run again with room.  Outside the copy-stream context, i.e. on
+                # the caller's (main) stream like every other launch that touches the workspace
+                Engine._contour_cap = n + n // 4
+                return self.contour_fetch(self.contour_launch(
+                    h["z"], h["mask"], h["x"], h["y"], h["level"], cap=n + n // 8))
+            Engine._contour_cap = max(Engine._contour_cap, n + n // 4)
+            out = []
+            with torch.cuda.stream(cs):
                 for key in ("cell", "ka", "kb", "pts"):
                     t = h[key][:n]
                     t.record_stream(cs)
                     host = torch.empty(t.shape, dtype=t.dtype, pin_memory=n > 4096)
                     host.copy_(t, non_blocking=True)
                     out.append(host)
-                cs.synchronize()
+            cs.synchronize()
         return tuple(t.numpy() for t in out)
 
     def contour_segments(self, z, mask, x, y, level=0.0):
@@ -520,15 +523,21 @@ class Engine:
             flat = values.reshape(-1)
             if not flat.is_contiguous():
                 flat = flat.contiguous()
-            res = self.empty(3)  # [a_lo, a_hi, nan count (uint64 bits)]
-            nbytes = int(nat.lib.dlb_select_scratch_bytes())
-            scratch = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            if getattr(self, "_select_bufs", None) is None:  # reused: a sweep calls this per slice
+                nbytes = int(nat.lib.dlb_select_scratch_bytes())
+                self._select_bufs = (self.empty(3), torch.empty(nbytes, dtype=torch.uint8,
+                                                                device=self.device),
+                                     torch.empty(3, dtype=_F64, pin_memory=True))
+            res, scratch, res_host = self._select_bufs  # res: [a_lo, a_hi, nan count (uint64 bits)]
+            nbytes = scratch.numel()
             ranks = (C.c_int64 * 2)(lo, hi)
             with self._timed("order_statistics", 17):
                 nat.check(nat.lib.dlb_order_statistics(
                     flat.data_ptr(), n, ranks, 2, res.data_ptr(), res[2:].data_ptr(),
                     scratch.data_ptr(), nbytes, self.stream()))
-            host = res.cpu()
+            res_host.copy_(res, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            host = res_host.clone()
         if int(host[2:].view(torch.int64)[0]) != 0:
             return float("nan")
         a, b = np.float64(host[0].item()), np.float64(host[1].item())

@@ -134,17 +134,21 @@ __global__ void __launch_bounds__(CT_BLOCK) contour_kernel(const ContourParams P
       P.cell[slot] = c;
       P.key_a[slot] = loa * nn + hia;
       P.key_b[slot] = lob * nn + hib;
-      // vertex on edge (p, q): p + f (q - p), f = (level - z_p) / (z_q - z_p)
-      const double fa = (P.level - zc[g.a0]) / (zc[g.a1] - zc[g.a0]);
-      const double fb = (P.level - zc[g.b0]) / (zc[g.b1] - zc[g.b0]);
+      // vertex on an edge, contourpy's expression (src/base_impl.h, interp(), linear z):
+      //   frac = (z1 - level) / (z1 - z0);  v = v0 * frac + v1 * (1 - frac)
+      // with point0 the edge's upper node (z > level; on the line's left) and point1 its lower
+      // node: (a0, a1) starts upper -> lower, (b0, b1) ends lower -> upper.  Separately rounded
+      // (no FMA contraction), like the C++ it restates and like oracle/contour_oracle.py.
+      const double fa = __ddiv_rn(__dsub_rn(zc[g.a1], P.level), __dsub_rn(zc[g.a1], zc[g.a0]));
+      const double fb = __ddiv_rn(__dsub_rn(zc[g.b0], P.level), __dsub_rn(zc[g.b0], zc[g.b1]));
+      const double ga = __dsub_rn(1.0, fa), gb = __dsub_rn(1.0, fb);
       const double xp = P.x[p % nx], xq = P.x[q % nx], yp = P.y[p / nx], yq = P.y[q / nx];
       const double xr = P.x[r % nx], xt = P.x[t % nx], yr = P.y[r / nx], yt = P.y[t / nx];
       double* o = P.pts + 4 * slot;
-      // separately rounded like numpy (no FMA contraction): bit-identical to the host tracer
-      o[0] = __dadd_rn(xp, __dmul_rn(fa, __dsub_rn(xq, xp)));
-      o[1] = __dadd_rn(yp, __dmul_rn(fa, __dsub_rn(yq, yp)));
-      o[2] = __dadd_rn(xr, __dmul_rn(fb, __dsub_rn(xt, xr)));
-      o[3] = __dadd_rn(yr, __dmul_rn(fb, __dsub_rn(yt, yr)));
+      o[0] = __dadd_rn(__dmul_rn(xp, fa), __dmul_rn(xq, ga));
+      o[1] = __dadd_rn(__dmul_rn(yp, fa), __dmul_rn(yq, ga));
+      o[2] = __dadd_rn(__dmul_rn(xt, fb), __dmul_rn(xr, gb));
+      o[3] = __dadd_rn(__dmul_rn(yt, fb), __dmul_rn(yr, gb));
     }
   }
 }

@@ -118,7 +118,13 @@ extern "C" int dlb_link_segments(const int64_t* h_cell, const int64_t* h_key_a,
         const int64_t lo = div_nn(kb), hi = kb - lo * nn;
         const int64_t j = div_x(lo), i = lo - j * xdim;
         int64_t c1 = -1, c2 = -1;
-        if (hi == lo + 1) {  // edge along x between nodes (j,i) (j,i+1): cells (j-1,i) and (j,i)
+        // The kind of grid edge decides where the neighbour lies - not cn - c, which is
+        // ambiguous on a one-cell-wide grid (xdim == 2: the cell above is c - 1).  hi == lo + 1
+        // is an x-edge only if lo is not in the last column: for xdim == 2 the diagonal of a
+        // corner-masked triangle, (j, 1)-(j+1, 0), has the same key difference.
+        bool along_x = false;
+        if (hi == lo + 1 && i < xdim - 1) {  // between nodes (j,i) (j,i+1): cells (j-1,i), (j,i)
+          along_x = true;
           if (j >= 1) c1 = (j - 1) * w + i;
           if (j < rows) c2 = j * w + i;
         } else if (hi == lo + xdim) {  // edge along y between (j,i) (j+1,i): cells (j,i-1), (j,i)
@@ -130,19 +136,19 @@ extern "C" int dlb_link_segments(const int64_t* h_cell, const int64_t* h_key_a,
         const int64_t cn = (c == c1) ? c2 : c1;
         if (cn < 0) continue;
         int64_t q = -1, q_end = 0;
-        if (cn == c + 1) {
+        if (!along_x && cn > c) {  // right neighbour, same row
           q = p + 1;
           q_end = row_start[r + 1];
           while (q < q_end && rec[q].cell == c) ++q;
-        } else if (cn == c - 1) {
+        } else if (!along_x) {  // left neighbour, same row
           q = p;
           while (q > row_start[r] && rec[q - 1].cell >= cn) --q;
           q_end = row_start[r + 1];
-        } else if (cn < c) {
+        } else if (cn < c) {  // row above
           while (cur_up < end_up && rec[cur_up].cell < cn) ++cur_up;
           q = cur_up;
           q_end = end_up;
-        } else {
+        } else {  // row below
           while (cur_dn < end_dn && rec[cur_dn].cell < cn) ++cur_dn;
           q = cur_dn;
           q_end = end_dn;

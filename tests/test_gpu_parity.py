@@ -660,7 +660,8 @@ def test_device_contour_segments_match_host_tracer(dl, golden):
     """csrc/contour.cu (cell classification on the device) + host linking gives exactly the
     polylines of the all-host tracer: the reference's ridge fields, random masked fields with
     saddles, single masked nodes (corner triangles), closed loops, non-finite values."""
-    from dynlab_b200._contour import marching_squares, zero_contour_lines_device
+    from dynlab_b200._contour import zero_contour_lines_device
+    from oracle.contour_oracle import marching_squares
     from dynlab_b200._engine import Engine
 
     eng = Engine.get()
