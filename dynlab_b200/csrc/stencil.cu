@@ -408,7 +408,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-template <int KIND, int MODE, bool XI, bool AOS>
+template <int KIND, int MODE, bool XI, bool AOS, bool UX, bool UY>
 __global__ void __launch_bounds__(TM_THREADS)
     stencil_tma_kernel(const StencilParams P, const __grid_constant__ CUtensorMap map0,
                        const __grid_constant__ CUtensorMap map1) {
@@ -429,7 +429,10 @@ __global__ void __launch_bounds__(TM_THREADS)
   if ((long long)blockIdx.x >= ntasks) return;
   const long long my_tasks = (ntasks - blockIdx.x + gridDim.x - 1) / gridDim.x;
   const long long total_stages = my_tasks * TM_SPT;
-  const bool ux = P.ax.uniform != 0, uy = P.ay.uniform != 0;
+  // np.gradient's uniform / non-uniform branch per axis is a template parameter: as a run-time
+  // flag it cost a predicated copy of both x formulas and a real branch around the y formula
+  // in every row
+  constexpr bool ux = UX, uy = UY;
   const double ix = P.ax.inv2h, iy = P.ay.inv2h;
 
   // producer side (thread 0): stage q of this CTA's stream = stage (q % TM_SPT) of its task q / TM_SPT
@@ -582,10 +585,10 @@ bool make_tile_map(CUtensorMap* map, const void* base, long long inner, long lon
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int KIND, int MODE, bool XI, bool AOS>
-int launch_tma(const StencilParams& P, const CUtensorMap& m0, const CUtensorMap& m1,
-               long long ntasks, cudaStream_t stream) {
-  auto kern = stencil_tma_kernel<KIND, MODE, XI, AOS>;
+template <int KIND, int MODE, bool XI, bool AOS, bool UX, bool UY>
+int launch_tma_uv(const StencilParams& P, const CUtensorMap& m0, const CUtensorMap& m1,
+                  long long ntasks, cudaStream_t stream) {
+  auto kern = stencil_tma_kernel<KIND, MODE, XI, AOS, UX, UY>;
   constexpr int dyn = TM_STAGES * TM_STAGE_BYTES;
   static int per_sm_of[DLB_MAX_DEVICES] = {0};  // the attribute is a per-device setting
   int dev = 0;
@@ -622,6 +625,18 @@ int ensure_logtab() {
   DLB_CUDA_CHECK(cudaMemcpyToSymbol(g_logtab, h, sizeof(h)));
   done[dev & (DLB_MAX_DEVICES - 1)] = true;
   return DLB_OK;
+}
+
+template <int KIND, int MODE, bool XI, bool AOS>
+int launch_tma(const StencilParams& P, const CUtensorMap& m0, const CUtensorMap& m1,
+               long long ntasks, cudaStream_t stream) {
+  if (P.ax.uniform && P.ay.uniform)
+    return launch_tma_uv<KIND, MODE, XI, AOS, true, true>(P, m0, m1, ntasks, stream);
+  if (P.ax.uniform)
+    return launch_tma_uv<KIND, MODE, XI, AOS, true, false>(P, m0, m1, ntasks, stream);
+  if (P.ay.uniform)
+    return launch_tma_uv<KIND, MODE, XI, AOS, false, true>(P, m0, m1, ntasks, stream);
+  return launch_tma_uv<KIND, MODE, XI, AOS, false, false>(P, m0, m1, ntasks, stream);
 }
 
 template <int KIND, int MODE, bool XI, class Loader>

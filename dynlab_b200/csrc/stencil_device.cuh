@@ -70,6 +70,25 @@ enum { KIND_FTLE = 0, KIND_EULER = 1 };
 // MODE of a KIND_FTLE kernel: plain, or with the peer stores of the fused gather
 enum { FTLE_PLAIN = 0, FTLE_PUSH = 1 };
 
+// Store under a predicate WITHOUT a branch.  `if (store) p[o] = v` lets the compiler wrap the
+// whole epilogue that produced v into a BSSY / BRA region per row (it did: the rows of a stage
+// were separate basic blocks, their dependent FP64 chains could not be interleaved; ncu's top
+// stall was the fixed-latency "wait").  An asm volatile store is executed unconditionally as far
+// as the optimiser knows, so the value is always computed and the rows of a stage stay ONE
+// basic block; the hardware predicate only suppresses the write.
+__device__ __forceinline__ void st_f64_if(double* p, double v, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.global.f64 [%0], %1;\n\t}" ::"l"(p),
+      "d"(v), "r"((int)pred)
+      : "memory");
+}
+__device__ __forceinline__ void st_u8_if(uint8_t* p, int v, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p st.global.u8 [%0], %1;\n\t}" ::"l"(p),
+      "r"(v), "r"((int)pred)
+      : "memory");
+}
+
 template <int KIND, int MODE>
 __device__ __forceinline__ void store_ftle(const StencilParams& P, long long o, double out) {
   P.field[o] = out;
@@ -452,7 +471,11 @@ __device__ __forceinline__ void emit_pred(const StencilParams& P, double2 C, dou
     double fl = fast_log_ge1_tab(lam, logtab);       // meaningless below 1, selected away
     fl = (lam < CUDART_INF) ? fl : lam;              // inf -> inf, NaN -> NaN like np.log
     const double out = (lam >= 1.0) ? P.scale * fl : ((lam != lam) ? lam : 0.0);
-    if (store) store_ftle<KIND, MODE>(P, o, out);
+    if constexpr (MODE == FTLE_PUSH) {
+      if (store) store_ftle<KIND, MODE>(P, o, out);  // + peer stores (the last rows of a slab only)
+    } else {
+      st_f64_if(P.field + o, out, store);
+    }
   } else if constexpr (KIND == KIND_EULER && !XI &&
                        (MODE == DLB_EULER_S_MIN || MODE == DLB_EULER_S_MAX)) {
     const double a = d0dx, d = d1dy, b = 0.5 * (d0dy + d1dx);
@@ -460,10 +483,8 @@ __device__ __forceinline__ void emit_pred(const StencilParams& P, double2 C, dou
     const double rad = fast_sqrt(fma(hm, hm, b * b));
     double out = (MODE == DLB_EULER_S_MAX) ? 0.5 * (a + d) + rad : 0.5 * (a + d) - rad;
     if (P.negate) out = -out;
-    if (store) {
-      P.field[o] = out;
-      if (P.mask) P.mask[o] = 0;
-    }
+    st_f64_if(P.field + o, out, store);
+    st_u8_if(P.mask + o, 0, store && P.mask != nullptr);
   } else {
     if (store) emit<KIND, MODE, XI>(P, C, d0dx, d1dx, d0dy, d1dy, o, logtab);
   }
