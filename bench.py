@@ -286,17 +286,21 @@ def extra_configs(eng, hbm_peak, world, rank, quick):
     from oracle import c_oracle as co
     from oracle import py_oracle as po
 
-    def ev_ms(fn, n=5, warm=2):
+    def ev_ms(fn, n=5, warm=2, inner=1):
+        """Median of n CUDA-event intervals around `inner` back-to-back calls, per call (sub-ms
+        kernels: inner > 1 keeps the queue full so the interval is device time)."""
         for _ in range(warm):
             fn()
         ts = []
         for _ in range(n):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
             e0.record()
-            fn()
+            for _ in range(inner):
+                fn()
             e1.record()
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
+            ts.append(e0.elapsed_time(e1) / inner)
         return float(np.median(ts))
 
     out = {}
@@ -311,12 +315,12 @@ def extra_configs(eng, hbm_peak, world, rank, quick):
             c2 = {"grid": [N, N], "edge_order": 2, "hbm_peak_gbs": hbm_peak, "kernels": {}}
             for name, mode, xi, nbytes in (("attraction_rate_s_min", nat.EULER_S_MIN, 0, 24),
                                            ("iles_eigen_s_min_xi", nat.EULER_S_MIN, 2, 40)):
-                ms = ev_ms(lambda: eng.euler_stencil(mode, u, v, 0, x, y, 2, 0, N, False, xi))
+                ms = ev_ms(lambda: eng.euler_stencil(mode, u, v, 0, x, y, 2, 0, N, False, xi), inner=10)
                 gbs = nbytes * N * N / ms / 1e6
                 c2["kernels"][name] = {"ms": ms, "bytes_per_point": nbytes, "GB_per_s": gbs,
                                        "frac_of_hbm_peak": gbs / hbm_peak}
             ms = ev_ms(lambda: eng.euler_stencil_flow(nat.EULER_S_MIN, fid, params, 0.0, x, y, 2,
-                                                      0, N, False, 0))
+                                                      0, N, False, 0), inner=10)
             c2["kernels"]["attraction_rate_fused_flow"] = {"ms": ms, "bytes_per_point": 8,
                                                            "GB_per_s": 8 * N * N / ms / 1e6}
             uh, vh = u.cpu().numpy(), v.cpu().numpy()

@@ -399,7 +399,7 @@ constexpr int TM_ROWS = TM_LOAD - 2;            // output rows per task (62)
 constexpr int TM_STAGES = DLB_TM_STAGES;        // stages in flight
 constexpr int TM_STAGE_BYTES = TM_RT * TM_THREADS * 16;
 #ifndef DLB_TM_MINB
-#define DLB_TM_MINB 5  // <= 102 registers: room for TM_RT rows in flight in the lockstep epilogue
+#define DLB_TM_MINB 5  // <= 102 registers (the Xi variants want ~90; 6 made them spill: +10 %)
 #endif
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1,
@@ -500,96 +500,47 @@ __global__ void __launch_bounds__(TM_THREADS, DLB_TM_MINB)
       while (!mbar_try_wait(&full[slot], parity)) {
       }
       const unsigned char* tile = tiles + slot * TM_STAGE_BYTES;
-      if constexpr (LockstepEpilogue<KIND, MODE, XI>::value) {
-        // gradients of the TM_RT centre rows first, then ONE lockstep epilogue for all of them
-        double gx0[TM_RT], gx1[TM_RT], gy0[TM_RT], gy1[TM_RT];
-        long long oo[TM_RT];
-        bool keep[TM_RT];
 #pragma unroll
-        for (int j = 0; j < TM_RT; ++j) {
-          double2 D, Ld, Rd;
-          if (AOS) {
-            const double2* row = reinterpret_cast<const double2*>(tile) + j * TM_THREADS;
-            D = row[t];
-            Ld = row[tl];
-            Rd = row[tr];
-          } else {
-            const double* ru = reinterpret_cast<const double*>(tile) + j * TM_THREADS;
-            const double* rv = ru + TM_RT * TM_THREADS;
-            D = make_double2(ru[t], rv[t]);
-            Ld = make_double2(ru[tl], rv[tl]);
-            Rd = make_double2(ru[tr], rv[tr]);
-          }
-          const int k = st * TM_RT + j - 2;  // output row of the centre held in C
-          if (ux) {
-            gx0[j] = (R.x - L.x) * ix;
-            gx1[j] = (R.y - L.y) * ix;
-          } else {
-            gx0[j] = fma(xc, R.x, fma(xb, C.x, xa * L.x));
-            gx1[j] = fma(xc, R.y, fma(xb, C.y, xa * L.y));
-          }
-          if (uy) {
-            gy0[j] = (D.x - U.x) * iy;
-            gy1[j] = (D.y - U.y) * iy;
-          } else {
-            const int kc = (k < 0) ? 0 : k;
-            const double2 yab = ysm[kc][0], ycz = ysm[kc][1];
-            gy0[j] = fma(ycz.x, D.x, fma(yab.y, C.x, yab.x * U.x));
-            gy1[j] = fma(ycz.x, D.y, fma(yab.y, C.y, yab.x * U.y));
-          }
-          oo[j] = o;
-          keep[j] = emit_thread && k >= 0 && k < nrows;
-          o += xdim;
-          U = C;
-          C = D;
-          L = Ld;
-          R = Rd;
+      for (int j = 0; j < TM_RT; ++j) {
+        double2 D, Ld, Rd;
+        if (AOS) {
+          const double2* row = reinterpret_cast<const double2*>(tile) + j * TM_THREADS;
+          D = row[t];
+          Ld = row[tl];
+          Rd = row[tr];
+        } else {
+          const double* ru = reinterpret_cast<const double*>(tile) + j * TM_THREADS;
+          const double* rv = ru + TM_RT * TM_THREADS;
+          D = make_double2(ru[t], rv[t]);
+          Ld = make_double2(ru[tl], rv[tl]);
+          Rd = make_double2(ru[tr], rv[tr]);
         }
-        emit_pred_n<KIND, MODE, XI, TM_RT>(P, gx0, gx1, gy0, gy1, oo,
-                                           KIND == KIND_FTLE ? logtab_s : nullptr, keep);
-      } else {
-  #pragma unroll
-        for (int j = 0; j < TM_RT; ++j) {
-          double2 D, Ld, Rd;
-          if (AOS) {
-            const double2* row = reinterpret_cast<const double2*>(tile) + j * TM_THREADS;
-            D = row[t];
-            Ld = row[tl];
-            Rd = row[tr];
-          } else {
-            const double* ru = reinterpret_cast<const double*>(tile) + j * TM_THREADS;
-            const double* rv = ru + TM_RT * TM_THREADS;
-            D = make_double2(ru[t], rv[t]);
-            Ld = make_double2(ru[tl], rv[tl]);
-            Rd = make_double2(ru[tr], rv[tr]);
-          }
-          const int k = st * TM_RT + j - 2;  // output row of the centre held in C
-          double d0dx, d1dx, d0dy, d1dy;
-          if (ux) {
-            d0dx = (R.x - L.x) * ix;
-            d1dx = (R.y - L.y) * ix;
-          } else {
-            d0dx = fma(xc, R.x, fma(xb, C.x, xa * L.x));
-            d1dx = fma(xc, R.y, fma(xb, C.y, xa * L.y));
-          }
-          if (uy) {
-            d0dy = (D.x - U.x) * iy;
-            d1dy = (D.y - U.y) * iy;
-          } else {
-            const int kc = (k < 0) ? 0 : k;
-            const double2 yab = ysm[kc][0], ycz = ysm[kc][1];
-            d0dy = fma(ycz.x, D.x, fma(yab.y, C.x, yab.x * U.x));
-            d1dy = fma(ycz.x, D.y, fma(yab.y, C.y, yab.x * U.y));
-          }
-          emit_pred<KIND, MODE, XI>(P, C, d0dx, d1dx, d0dy, d1dy, o,
-                                    KIND == KIND_FTLE ? logtab_s : nullptr,
-                                    emit_thread && k >= 0 && k < nrows);
-          o += xdim;
-          U = C;
-          C = D;
-          L = Ld;
-          R = Rd;
+        const int k = st * TM_RT + j - 2;  // output row of the centre held in C
+        double d0dx, d1dx, d0dy, d1dy;
+        if (ux) {
+          d0dx = (R.x - L.x) * ix;
+          d1dx = (R.y - L.y) * ix;
+        } else {
+          d0dx = fma(xc, R.x, fma(xb, C.x, xa * L.x));
+          d1dx = fma(xc, R.y, fma(xb, C.y, xa * L.y));
         }
+        if (uy) {
+          d0dy = (D.x - U.x) * iy;
+          d1dy = (D.y - U.y) * iy;
+        } else {
+          const int kc = (k < 0) ? 0 : k;
+          const double2 yab = ysm[kc][0], ycz = ysm[kc][1];
+          d0dy = fma(ycz.x, D.x, fma(yab.y, C.x, yab.x * U.x));
+          d1dy = fma(ycz.x, D.y, fma(yab.y, C.y, yab.x * U.y));
+        }
+        emit_pred<KIND, MODE, XI>(P, C, d0dx, d1dx, d0dy, d1dy, o,
+                                  KIND == KIND_FTLE ? logtab_s : nullptr,
+                                  emit_thread && k >= 0 && k < nrows);
+        o += xdim;
+        U = C;
+        C = D;
+        L = Ld;
+        R = Rd;
       }
       // every thread has read this stage: hand its slot back to the TMA unit
       __syncthreads();

@@ -67,6 +67,10 @@ constexpr int ST_ROWS = 32;  // rows per warp task
 
 
 enum { KIND_FTLE = 0, KIND_EULER = 1 };
+// build-time switch of the tile kernel's epilogue stores (see st_f64_if below)
+#ifndef DLB_ASM_STORE
+#define DLB_ASM_STORE 1
+#endif
 // MODE of a KIND_FTLE kernel: plain, or with the peer stores of the fused gather
 enum { FTLE_PLAIN = 0, FTLE_PUSH = 1 };
 
@@ -471,7 +475,7 @@ __device__ __forceinline__ void emit_pred(const StencilParams& P, double2 C, dou
     double fl = fast_log_ge1_tab(lam, logtab);       // meaningless below 1, selected away
     fl = (lam < CUDART_INF) ? fl : lam;              // inf -> inf, NaN -> NaN like np.log
     const double out = (lam >= 1.0) ? P.scale * fl : ((lam != lam) ? lam : 0.0);
-    if constexpr (MODE == FTLE_PUSH) {
+    if constexpr (MODE == FTLE_PUSH || !DLB_ASM_STORE) {
       if (store) store_ftle<KIND, MODE>(P, o, out);  // + peer stores (the last rows of a slab only)
     } else {
       st_f64_if(P.field + o, out, store);
@@ -483,135 +487,17 @@ __device__ __forceinline__ void emit_pred(const StencilParams& P, double2 C, dou
     const double rad = fast_sqrt(fma(hm, hm, b * b));
     double out = (MODE == DLB_EULER_S_MAX) ? 0.5 * (a + d) + rad : 0.5 * (a + d) - rad;
     if (P.negate) out = -out;
+#if DLB_ASM_STORE
     st_f64_if(P.field + o, out, store);
     st_u8_if(P.mask + o, 0, store && P.mask != nullptr);
+#else
+    if (store) {
+      P.field[o] = out;
+      if (P.mask) P.mask[o] = 0;
+    }
+#endif
   } else {
     if (store) emit<KIND, MODE, XI>(P, C, d0dx, d1dx, d0dy, d1dy, o, logtab);
-  }
-}
-
-// ---- the same epilogue for NR rows in lockstep ------------------------------------------------
-// ptxas keeps the rows of an unrolled stage in source order: even as one basic block the four
-// epilogues ran one after the other, each a chain of ~40 dependent FP64 instructions (sqrt by
-// Goldschmidt, log by table + Horner), and the fixed-latency "wait" stayed the top stall.  Here
-// every step of the chain is written for all NR rows before the next step starts, so NR
-// independent instructions sit between an instruction and its consumer (the way dmath.cuh
-// interleaves the polynomial chains of the integrator's sines).  Same operations in the same
-// order per point as emit_pred: bit-identical results.
-template <int NR>
-__device__ __forceinline__ void fast_sqrt_n(const double (&x)[NR], double (&g)[NR]) {
-  double r[NR], h[NR], e[NR];
-#pragma unroll
-  for (int j = 0; j < NR; ++j) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r[j]) : "d"(x[j]));
-#pragma unroll
-  for (int j = 0; j < NR; ++j) g[j] = x[j] * r[j];
-#pragma unroll
-  for (int j = 0; j < NR; ++j) h[j] = 0.5 * r[j];
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-#pragma unroll
-    for (int j = 0; j < NR; ++j) e[j] = fma(-h[j], g[j], 0.5);
-#pragma unroll
-    for (int j = 0; j < NR; ++j) g[j] = fma(g[j], e[j], g[j]);
-#pragma unroll
-    for (int j = 0; j < NR; ++j) h[j] = fma(h[j], e[j], h[j]);
-  }
-#pragma unroll
-  for (int j = 0; j < NR; ++j) e[j] = fma(-g[j], g[j], x[j]);
-#pragma unroll
-  for (int j = 0; j < NR; ++j) g[j] = fma(e[j], h[j], g[j]);
-#pragma unroll
-  for (int j = 0; j < NR; ++j) g[j] = (x[j] > 0.0) ? g[j] : 0.0;
-}
-
-template <int NR>
-__device__ __forceinline__ void fast_log_ge1_tab_n(const double (&x)[NR], const double2* tab,
-                                                   double (&out)[NR]) {
-  double m[NR], r[NR], q[NR], ed[NR], ty[NR];
-#pragma unroll
-  for (int j = 0; j < NR; ++j) {
-    const int hi = __double2hiint(x[j]);
-    ed[j] = (double)((hi >> 20) - 1023);
-    m[j] = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x[j]));
-    const double2 t = tab[(hi >> 13) & 0x7f];
-    r[j] = t.x;
-    ty[j] = t.y;
-  }
-#pragma unroll
-  for (int j = 0; j < NR; ++j) r[j] = fma(m[j], r[j], -1.0);
-#pragma unroll
-  for (int j = 0; j < NR; ++j) q[j] = ST_LOGK[12];
-#pragma unroll
-  for (int k = 13; k <= 18; ++k) {
-#pragma unroll
-    for (int j = 0; j < NR; ++j) q[j] = fma(q[j], r[j], ST_LOGK[k]);  // -1/8 ... -1/2
-  }
-#pragma unroll
-  for (int j = 0; j < NR; ++j) {
-    const double hi_part = fma(ed[j], ST_LOGK[9], ty[j]);
-    const double lo_part = fma(ed[j], ST_LOGK[10], fma(r[j] * r[j], q[j], r[j]));
-    out[j] = hi_part + lo_part;
-  }
-}
-
-// true when emit_pred_n covers this variant (the branch-free epilogues)
-template <int KIND, int MODE, bool XI>
-struct LockstepEpilogue {
-  static constexpr bool value =
-      !XI && ((KIND == KIND_FTLE && MODE == FTLE_PLAIN) ||
-              (KIND == KIND_EULER && (MODE == DLB_EULER_S_MIN || MODE == DLB_EULER_S_MAX)));
-};
-
-// o[j]: output offsets; store[j]: store predicates
-template <int KIND, int MODE, bool XI, int NR>
-__device__ __forceinline__ void emit_pred_n(const StencilParams& P, const double (&d0dx)[NR],
-                                            const double (&d1dx)[NR], const double (&d0dy)[NR],
-                                            const double (&d1dy)[NR], const long long (&o)[NR],
-                                            const double2* logtab, const bool (&store)[NR]) {
-  static_assert(LockstepEpilogue<KIND, MODE, XI>::value, "variant has no lockstep epilogue");
-  if constexpr (KIND == KIND_FTLE) {
-    double c11[NR], c12[NR], c22[NR], hm[NR], rad2[NR], rad[NR], lam[NR], fl[NR];
-#pragma unroll
-    for (int j = 0; j < NR; ++j) c11[j] = fma(d0dx[j], d0dx[j], d1dx[j] * d1dx[j]);
-#pragma unroll
-    for (int j = 0; j < NR; ++j) c12[j] = fma(d0dx[j], d0dy[j], d1dx[j] * d1dy[j]);
-#pragma unroll
-    for (int j = 0; j < NR; ++j) c22[j] = fma(d0dy[j], d0dy[j], d1dy[j] * d1dy[j]);
-#pragma unroll
-    for (int j = 0; j < NR; ++j) hm[j] = 0.5 * (c11[j] - c22[j]);
-#pragma unroll
-    for (int j = 0; j < NR; ++j) rad2[j] = fma(hm[j], hm[j], c12[j] * c12[j]);
-    fast_sqrt_n<NR>(rad2, rad);
-#pragma unroll
-    for (int j = 0; j < NR; ++j) lam[j] = 0.5 * (c11[j] + c22[j]) + rad[j];
-    fast_log_ge1_tab_n<NR>(lam, logtab, fl);  // meaningless below 1, selected away
-#pragma unroll
-    for (int j = 0; j < NR; ++j) {
-      const double f = (lam[j] < CUDART_INF) ? fl[j] : lam[j];  // inf -> inf, NaN -> NaN
-      const double out = (lam[j] >= 1.0) ? P.scale * f : ((lam[j] != lam[j]) ? lam[j] : 0.0);
-      st_f64_if(P.field + o[j], out, store[j]);
-    }
-  } else {
-    double a[NR], d[NR], b[NR], hm[NR], rad2[NR], rad[NR];
-#pragma unroll
-    for (int j = 0; j < NR; ++j) {
-      a[j] = d0dx[j];
-      d[j] = d1dy[j];
-      b[j] = 0.5 * (d0dy[j] + d1dx[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < NR; ++j) hm[j] = 0.5 * (a[j] - d[j]);
-#pragma unroll
-    for (int j = 0; j < NR; ++j) rad2[j] = fma(hm[j], hm[j], b[j] * b[j]);
-    fast_sqrt_n<NR>(rad2, rad);
-#pragma unroll
-    for (int j = 0; j < NR; ++j) {
-      double out = (MODE == DLB_EULER_S_MAX) ? 0.5 * (a[j] + d[j]) + rad[j]
-                                             : 0.5 * (a[j] + d[j]) - rad[j];
-      if (P.negate) out = -out;
-      st_f64_if(P.field + o[j], out, store[j]);
-      st_u8_if(P.mask + o[j], 0, store[j] && P.mask != nullptr);
-    }
   }
 }
 

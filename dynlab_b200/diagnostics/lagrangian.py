@@ -369,6 +369,10 @@ class FTLE(LagrangianDiagnostic2D):
             m, s = run["m"], run["s"]
             if run["tail"]:
                 mark(run, "halo pushed", run["main"])
+                if not G.multiprocess:  # see wait_gathered below: stream dependency, no spinning
+                    for other in runs:
+                        if abs(other["m"].rank - m.rank) == 1:
+                            run["main"].wait_stream(other["main"])
                 G.halo_wait(m, slabs, gen, run["main"].cuda_stream)
                 mark(run, "halo arrived", run["main"])
                 for k, (a, b) in enumerate(run["tail"]):
@@ -385,6 +389,12 @@ class FTLE(LagrangianDiagnostic2D):
         if target == "device":
             for run in runs:
                 if dests is None or run["m"].rank in dests:
+                    if not G.multiprocess:
+                        # one process: every member's departures are also stream dependencies
+                        # (cross-device events), so the flag wait below never has to spin
+                        for other in runs:
+                            run["main"].wait_stream(other["m"].engine.copy_stream)
+                            run["main"].wait_stream(other["main"])
                     G.wait_gathered(run["m"], gen, run["main"].cuda_stream)
                     mark(run, "all rows gathered", run["main"])
             self.field_device = first["out"]

@@ -9,5 +9,5 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 "$NVCC" -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC "$@" \
   -c "$HERE/stencil.cu" -o "$HERE/_obj/stencil_$name.o"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$HERE/../_lib/$name.so" \
-  "$HERE"/_obj/{capi,rk45,floweval,contour,select,link,eulerflow}.o "$HERE/_obj/stencil_$name.o"
+  "$HERE"/_obj/{capi,rk45,floweval,contour,select,link,eulerflow,peer}.o "$HERE/_obj/stencil_$name.o"
 echo "built $name.so"

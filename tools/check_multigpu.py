@@ -7,8 +7,11 @@ private copy), slab cut (by rows, by integrator work) and for the device-residen
 
 --full adds BASELINE config 3 (8192x4096, t=(10,0)), also checked against the C oracle on the
 every-64th-row/column sample.  --backend gloo --same-device puts every rank on cuda:0 (CUDA IPC
-between processes sharing one GPU): the multi-process data path on a 1-GPU box; torch.distributed
-then only carries the plumbing, so the NCCL transport is skipped.
+between processes sharing one GPU; torch.distributed only carries the plumbing, so the NCCL
+transport is skipped).  HAZARD: the ranks' wait kernels then spin on flags written by other
+processes of the SAME GPU, which only works as long as the driver time-slices them; the
+profiling guide reports Xid 109 (context-switch timeout) for that pattern, so no test runs it -
+it is a manual debugging aid.
 """
 import argparse
 import hashlib
