@@ -48,7 +48,7 @@ F_RHS = 18 + 5 * 20
 F_ATTEMPT = 6 * F_RHS + 64 * 2 + 16 + 20   # 872
 F_SEED = 2 * F_RHS + 10 * 2                # 256
 BYTES_PER_POINT_K2 = 24
-TRAFFIC_FILE = "r01_traffic.json"
+TRAFFIC_FILE = "r02_traffic.json"
 
 
 def grid(stride: int = 1):
@@ -641,7 +641,7 @@ def run_ours(args):
                                  "(dlb_dfma_peak), theoretical 37.2 TFLOP/s at 1965 MHz"},
             "roofline_hbm": {"bound": "hbm", "achieved": k2_gbs, "peak": hbm_peak, "unit": "GB/s",
                              "frac": k2_gbs / hbm_peak,
-                             "traffic": dram("stencil_interior_kernel_ftle"), "traffic_source": src,
+                             "traffic": dram("stencil_tma_kernel_ftle"), "traffic_source": src,
                              "kernel": "stencil_tma_kernel<FTLE> + stencil_edge_kernel (K2)",
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         }
