@@ -327,7 +327,9 @@ __device__ __forceinline__ double fast_sqrt(double x) {
   g = fma(g, e, g);
   h = fma(h, e, h);
   g = fma(fma(-g, g, x), h, g);
-  return (x > 0.0) ? g : 0.0;
+  // x == 0 (rsqrt = inf, g = NaN) -> 0.  Tested on the high word: an integer compare costs one
+  // issue slot, an FP64 compare two (x >= 0 or NaN here; a NaN's high word passes and g is NaN).
+  return (__double2hiint(x) >= 0x00100000) ? g : 0.0;
 }
 
 // Constants of fast_log_ge1 in constant memory (a 64-bit literal costs two UMOVs per use on
@@ -472,9 +474,14 @@ __device__ __forceinline__ void emit_pred(const StencilParams& P, double2 C, dou
     const double c22 = fma(d0dy, d0dy, d1dy * d1dy);
     const double hm = 0.5 * (c11 - c22);
     const double lam = 0.5 * (c11 + c22) + fast_sqrt(fma(hm, hm, c12 * c12));
-    double fl = fast_log_ge1_tab(lam, logtab);       // meaningless below 1, selected away
-    fl = (lam < CUDART_INF) ? fl : lam;              // inf -> inf, NaN -> NaN like np.log
-    const double out = (lam >= 1.0) ? P.scale * fl : ((lam != lam) ? lam : 0.0);
+    const double fl = fast_log_ge1_tab(lam, logtab);  // meaningless below 1, selected away
+    // lam >= 0, +inf or NaN.  Classified on the high word (integer compares: one issue slot
+    // each instead of two per FP64 compare): [0x3ff00000, 0x7ff00000) finite >= 1 -> scale *
+    // ln(lam); >= 0x7ff00000 (unsigned: +inf, NaN of either sign) -> scale * lam = inf / NaN like
+    // np.log; below -> 0   (lagrangian.py:70-73)
+    const unsigned lh = (unsigned)__double2hiint(lam);
+    const double picked = (lh >= 0x7ff00000u) ? lam : fl;
+    const double out = (lh >= 0x3ff00000u) ? P.scale * picked : 0.0;
     if constexpr (MODE == FTLE_PUSH || !DLB_ASM_STORE) {
       if (store) store_ftle<KIND, MODE>(P, o, out);  // + peer stores (the last rows of a slab only)
     } else {
