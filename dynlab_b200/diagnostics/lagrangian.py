@@ -319,6 +319,7 @@ class FTLE(LagrangianDiagnostic2D):
         # chunk-major over the local members, so that every device has work queued before the
         # host moves on to the next chunk
         overlap = bool(self.overlap_chunks)
+        side = bool(self.side_stencil) and not overlap
         for run in runs:
             eng = run["m"].engine
             run["k1_streams"] = [run["main"], eng.alt_stream] if overlap else [run["main"]]
@@ -326,6 +327,7 @@ class FTLE(LagrangianDiagnostic2D):
             run["k1_events"] = []
             if overlap:
                 eng.alt_stream.wait_stream(run["main"])
+            if overlap or side:
                 eng.stencil_stream.wait_stream(run["main"])
         for c in range(max([len(r["steps"]) for r in runs] + [0])):
             for run in runs:
@@ -348,17 +350,28 @@ class FTLE(LagrangianDiagnostic2D):
                 mark(run, f"K1 rows {r0}:{r1} done", k1s)
                 if upto > done:
                     k2s = run["k2_stream"]
+                    left = len(run["steps"]) - 1 - c  # chunks still to come
                     if overlap:
                         for ev in run["k1_events"][-2:]:
                             k2s.wait_event(ev)
-                    left = len(run["steps"]) - 1 - c  # chunks still to come
+                    elif side and left > 0:
+                        # K2 of a chunk that is not the last: on the priority stencil stream,
+                        # enqueued before the next K1 - both become ready when this K1 ends, K2's
+                        # CTAs are picked first and the next K1 fills the SMs around them, so K2
+                        # costs the main stream nothing
+                        with torch.cuda.device(m.device):
+                            ev = torch.cuda.Event()
+                            ev.record(run["main"])
+                            m.engine.stencil_stream.wait_event(ev)
+                        k2s = m.engine.stencil_stream
                     last = left == 0 and not run["tail"]
                     produce(run, run["steps"][0][0], r1, done, upto, last,
                             left < self.fused_gather_chunks, k2s)
-        if overlap:
+        if overlap or side:
             for run in runs:
                 eng = run["m"].engine
-                run["main"].wait_stream(eng.alt_stream)
+                if overlap:
+                    run["main"].wait_stream(eng.alt_stream)
                 run["main"].wait_stream(eng.stencil_stream)
         # 1-row halo exchange (dlb_halo_exchange: every member pushes first, then waits), then the
         # rows that were waiting for it
@@ -444,6 +457,9 @@ class FTLE(LagrangianDiagnostic2D):
     # K1 chunks on alternating streams (chunk c+1 fills the SMs as chunk c drains), K2 on its own
     # high-priority stream; False: everything in order on one stream (K2 between the chunks)
     overlap_chunks = False
+    # K2 of every chunk but the last on the priority stencil stream (runs beside the start of
+    # the next K1 instead of between the two K1 launches)
+    side_stencil = True
     trace = None  # set to [] to collect (rank, label, timed CUDA event) of the next group call
     # device result: the K2 launches of this many last chunks (and of the rows that wait for a
     # halo exchange) store straight into the other GPUs' fields (dlb_ftle_stencil_gather);

@@ -997,6 +997,96 @@ def test_multi_gpu_sharding_matches_single(dl):
     _torchrun_check(min(n, 4), [], 29617)
 
 
+def test_peer_abi_on_one_device(dl):
+    """The multi-GPU entry points of the C-ABI called directly (ctypes, raw pointers), with two
+    "members" on cuda:0: symmetric blocks, IPC handle export, row gather push + flag release,
+    flag wait (already satisfied: no spinning), halo exchange, one-sided peer copy, and K2 fused
+    with the gather (peer stores from the epilogue) against the plain K2."""
+    import ctypes as C
+
+    from dynlab_b200 import _native as nat
+    from dynlab_b200._engine import Engine
+    from dynlab_b200.peer import _Raw
+
+    eng = Engine.get()
+    lib = nat.lib
+    n = C.c_int(0)
+    nat.check(lib.dlb_device_count(C.byref(n)))
+    assert n.value == torch.cuda.device_count()
+    nat.check(lib.dlb_peer_enable(0, 0))
+    stream = torch.cuda.current_stream().cuda_stream
+    rows, xdim = 6, 40
+    nbytes = rows * xdim * 8
+    blocks = []
+    for _ in range(2):
+        p = C.c_void_p()
+        nat.check(lib.dlb_peer_alloc(nbytes + 256, C.byref(p)))
+        blocks.append(p.value)
+    t = [torch.as_tensor(_Raw(b, nbytes + 256), device=eng.device) for b in blocks]
+    assert all(int(x.sum()) == 0 for x in t)  # zero-filled
+    handle = C.create_string_buffer(nat.IPC_HANDLE_BYTES)
+    nat.check(lib.dlb_ipc_export(blocks[0], handle))
+    assert any(handle.raw)
+    a = t[0][:nbytes].view(torch.float64).view(rows, xdim)
+    b = t[1][:nbytes].view(torch.float64).view(rows, xdim)
+    a.copy_(torch.arange(rows * xdim, dtype=torch.float64, device=eng.device).view(rows, xdim))
+    flags = [blk + nbytes for blk in blocks]  # uint64 words behind the rows
+    # rows 1..3 of block 0 -> same place of block 1, then flag 7 in both
+    off = 1 * xdim * 8
+    dst = (C.c_void_p * 2)(blocks[0] + off, blocks[1] + off)
+    flg = (C.c_void_p * 2)(flags[0], flags[1])
+    nat.check(lib.dlb_gather_rows(blocks[0] + off, 3 * xdim * 8, dst, 2, flg, 7, stream))
+    nat.check(lib.dlb_wait_flags(flags[1], 1, 7, 5.0, None, stream))
+    timed_out = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+    nat.check(lib.dlb_wait_flags(flags[0], 1, 7, 5.0, timed_out.data_ptr(), stream))
+    torch.cuda.synchronize()
+    assert int(timed_out[0]) == 0
+    assert torch.equal(b[1:4], a[1:4]) and float(b[0].abs().sum()) == 0 and float(b[4:].abs().sum()) == 0
+    fl = t[1][nbytes:nbytes + 8].view(torch.int64)
+    assert int(fl[0]) == 7
+    # a wait for a value nobody publishes gives up and reports (bounded, no hang)
+    nat.check(lib.dlb_wait_flags(flags[1], 1, 99, 0.05, timed_out.data_ptr(), stream))
+    torch.cuda.synchronize()
+    assert int(timed_out[0]) == 1
+    # halo exchange: first own row (1) -> "up" slot, last own row (4) -> "down" slot, flags 3
+    up = torch.zeros(xdim, dtype=torch.float64, device=eng.device)
+    down = torch.zeros(xdim, dtype=torch.float64, device=eng.device)
+    nat.check(lib.dlb_halo_exchange(blocks[0], xdim * 8, 1, 4, up.data_ptr(), down.data_ptr(),
+                                    flags[0] + 8, flags[1] + 8, 3, stream))
+    torch.cuda.synchronize()
+    assert torch.equal(up, a[1]) and torch.equal(down, a[4])
+    assert int(t[0][nbytes + 8:nbytes + 16].view(torch.int64)[0]) == 3
+    # one-sided copy
+    c = torch.zeros(2, xdim, dtype=torch.float64, device=eng.device)
+    nat.check(lib.dlb_peer_copy(c.data_ptr(), blocks[0] + 2 * xdim * 8, 2 * xdim * 8, stream))
+    torch.cuda.synchronize()
+    assert torch.equal(c, a[2:4])
+    # argument errors
+    assert lib.dlb_gather_rows(blocks[0], 8, dst, 99, flg, 1, stream) == nat.DLB_ERR_ARG
+    assert lib.dlb_wait_flags(flags[0], 1, 1, -1.0, None, stream) == nat.DLB_ERR_ARG
+    for blk in blocks:
+        nat.check(lib.dlb_peer_free(blk))
+    # K2 fused with the gather == plain K2, in the local field and in two "peer" fields
+    rng = np.random.default_rng(5)
+    for (ny, nx, eo) in ((40, 300, 2), (7, 131, 1)):
+        x, y = np.sort(rng.uniform(0, 2, nx)), np.linspace(0, 1, ny)
+        fm = torch.tensor(rng.normal(size=(ny, nx, 2)), device=eng.device)
+        ref, _ = eng.ftle_stencil(fm, 0, x, y, eo, 3.0, 0, ny)
+        loc = eng.empty(ny, nx)
+        peers = [torch.full((ny, nx), -1.0, dtype=torch.float64, device=eng.device) for _ in range(2)]
+        fl = torch.zeros(4, dtype=torch.int64, device=eng.device)
+        r0, r1 = 2, ny - 1  # a slab in the middle: only these rows are produced and pushed
+        eng.ftle_stencil_gather(fm, 0, x, y, eo, 3.0, r0, r1 - r0, loc[r0:r1],
+                                [p[r0:r1].data_ptr() for p in peers],
+                                [fl[k:].data_ptr() for k in range(3)], 41)
+        torch.cuda.synchronize()
+        assert torch.equal(loc[r0:r1], ref[r0:r1])
+        for p_ in peers:
+            assert torch.equal(p_[r0:r1], ref[r0:r1])
+            assert float((p_[:r0] + 1).abs().sum()) == 0 and float((p_[r1:] + 1).abs().sum()) == 0
+        assert fl.tolist() == [41, 41, 41, 0]
+
+
 def test_single_process_group_matches_single_device(dl):
     """One plain process driving a group of GPUs (the reference creates and tears
     down its parallelism inside one blocking call, R:_base_classes.py:139-148).  With one GPU

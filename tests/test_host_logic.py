@@ -62,6 +62,38 @@ def test_abi_argument_errors_without_gpu():
     assert rc == nat.DLB_ERR_TOO_SMALL
 
 
+def test_peer_abi_argument_errors_without_gpu():
+    """The multi-GPU helpers validate their arguments before any CUDA call."""
+    import ctypes as C
+
+    from dynlab_b200 import _native as nat
+
+    lib = nat.lib
+    assert lib.dlb_device_count(None) == nat.DLB_ERR_ARG
+    assert lib.dlb_peer_alloc(16, None) == nat.DLB_ERR_ARG
+    assert lib.dlb_ipc_export(None, None) == nat.DLB_ERR_ARG
+    assert lib.dlb_ipc_open(None, None) == nat.DLB_ERR_ARG
+    assert lib.dlb_peer_copy(None, None, 8, None) == nat.DLB_ERR_ARG
+    assert lib.dlb_peer_copy(None, None, 0, None) == nat.DLB_OK  # nothing to copy
+    dst = (C.c_void_p * 1)(None)
+    assert lib.dlb_gather_rows(None, 8, dst, 1, dst, 1, None) == nat.DLB_ERR_ARG
+    assert lib.dlb_gather_rows(None, 0, dst, nat.MAX_PEERS + 1, dst, 1, None) == nat.DLB_ERR_ARG
+    assert lib.dlb_gather_rows(None, 0, dst, 1, dst, 1, None) == nat.DLB_OK  # no rows, no flags
+    assert lib.dlb_halo_exchange(None, 8, 0, 0, None, None, None, None, 1, None) == nat.DLB_ERR_ARG
+    assert lib.dlb_wait_flags(None, 0, 1, 1.0, None, None) == nat.DLB_OK
+    assert lib.dlb_wait_flags(None, 1, 1, 1.0, None, None) == nat.DLB_ERR_ARG
+    assert lib.dlb_wait_flags(8, 33, 1, 1.0, None, None) == nat.DLB_ERR_ARG
+    assert b"dlb_wait_flags" in lib.dlb_last_error()
+    x = np.linspace(0, 1, 4)
+    rc = lib.dlb_ftle_stencil_gather(None, 4, 0, nat.dptr(x), 4, nat.dptr(x), 4, 2, 1.0, 0, 4, None,
+                                     None, 0, None, 0, 1, 8, 1 << 20, None)
+    assert rc == nat.DLB_ERR_ARG
+    p = nat.darray([0.1, 0.2])
+    rc = lib.dlb_flowmap_rk45_resident(0, p, 2, 8, 4, 8, 0, 4, 0.0, 1.0, 1e-6, 1e-6, np.inf, 0.0, 8,
+                                       None, None, 8, 8, 1 << 20, None)
+    assert rc == nat.DLB_ERR_ARG and b"parameter count" in lib.dlb_last_error()
+
+
 # ------------------------------------------------------------------ flows / resolver / utils
 def test_host_flows_reference_vectors():
     from dynlab_b200 import flows

@@ -37,7 +37,7 @@ eng = Engine.get()
 
 
 def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=True, overlap=None,
-        fused=1, hchunks=4):
+        fused=1, hchunks=4, side=True):
     if args.only and args.only not in name:
         return
     sharding.set_transport(transport)
@@ -48,6 +48,7 @@ def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=Tru
     if overlap is not None:
         d.overlap_chunks = overlap
     d.fused_gather_chunks = fused
+    d.side_stencil = side
     for _ in range(3):
         d.compute_device(x, y, double_gyre, (10, 0), **kw)
     dist.barrier()
@@ -69,7 +70,7 @@ def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=Tru
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     out = {"variant": name, "transport": transport, "halo": halo, "chunks": list(chunks) if isinstance(chunks, tuple) else chunks, "last_fraction": frac,
-           "weighted": weighted, "overlap": overlap, "fused": fused, "ms_per_step": float(tmax[0]),
+           "weighted": weighted, "overlap": overlap, "fused": fused, "side": side, "host_chunks": list(hchunks) if isinstance(hchunks, tuple) else hchunks, "ms_per_step": float(tmax[0]),
            "k1_ms_max_rank": float(tmax[1]), "k1_ms_min_rank": float(tmin[1]),
            "sha": hashlib.sha256(f.cpu().numpy().tobytes()).hexdigest()[:16]}
     if args.trace and transport == "peer":
@@ -107,18 +108,14 @@ def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=Tru
 
 
 run("nccl after the kernels (round 1)", transport="nccl")
-run("peer, 2 chunks .875/.125", chunks=(0.875, 0.125))
-run("peer, 2 chunks .875/.125, redundant", chunks=(0.875, 0.125), halo="redundant")
-run("peer, 2 chunks .9/.1, redundant", chunks=(0.9, 0.1), halo="redundant")
-run("peer, 2 chunks .9375/.0625, redundant", chunks=(0.9375, 0.0625), halo="redundant")
-run("peer, 3 chunks .5/.4/.1, redundant", chunks=(0.5, 0.4, 0.1), halo="redundant")
-run("peer, 2 chunks .875/.125, redundant, DMA only", chunks=(0.875, 0.125), halo="redundant", fused=0)
-run("peer, 2 chunks .875/.125, overlap, redundant", chunks=(0.875, 0.125), halo="redundant", overlap=True)
-run("peer, 4 chunks, overlap, fused 1, redundant", overlap=True, fused=1, halo="redundant", chunks=4)
-run("peer, 3 chunks .6/.3/.1, overlap, fused 1, redundant", overlap=True, fused=1, halo="redundant",
-    chunks=(0.6, 0.3, 0.1))
+run("default (2 chunks .875/.125, redundant, side stencil)", chunks=(0.875, 0.125), halo="redundant")
+run("default, K2 between the K1 launches", chunks=(0.875, 0.125), halo="redundant", side=False)
+run("default, exchange halo", chunks=(0.875, 0.125), halo="exchange")
+run("2 chunks .9/.1", chunks=(0.9, 0.1), halo="redundant")
+run("3 chunks .5/.4/.1", chunks=(0.5, 0.4, 0.1), halo="redundant")
+run("host chunks 3", hchunks=3, halo="redundant")
 run("host chunks 4", hchunks=4, halo="redundant")
-run("host chunks 5", hchunks=5, halo="redundant")
-run("host chunks 6/48", hchunks=6, frac=48, halo="redundant")
-run("host chunks 4, overlap", hchunks=4, halo="redundant", overlap=True)
+run("host chunks 4, K2 between", hchunks=4, halo="redundant", side=False)
+run("host chunks (.4,.3,.2,.1)", hchunks=(0.4, 0.3, 0.2, 0.1), halo="redundant")
+run("host chunks (.35,.3,.25,.07,.03)", hchunks=(0.35, 0.3, 0.25, 0.07, 0.03), halo="redundant")
 dist.destroy_process_group()
