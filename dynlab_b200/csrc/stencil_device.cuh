@@ -313,17 +313,17 @@ struct LoaderSoA {
   }
 };
 
-// sqrt(x) for finite x >= 0: MUFU.RSQ64H seed + two coupled Newton (Goldschmidt) steps and a
-// final residual correction; 0 maps to 0.  No special-case branches (the library routine's
-// slow-path test is what the HBM-bound kernels cannot afford).
+// sqrt(x) for finite x >= 0: MUFU.RSQ64H seed (~2^-20), ONE coupled Newton (Goldschmidt) step
+// (g ~ sqrt x and h ~ 1 / (2 sqrt x) to ~2^-39) and a final residual step g + (x - g^2) h, which
+// is itself a Newton step and squares the error again (2^-78: the result is rounding only,
+// <= 1 ulp).  Round 1 ran two Goldschmidt steps before the residual one; the second bought
+// nothing (3 FP64 instructions of ~55 per FTLE point on an FP64-issue-bound kernel).  0 maps
+// to 0.  No special-case branches.
 __device__ __forceinline__ double fast_sqrt(double x) {
   double r;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
   double g = x * r, h = 0.5 * r;
-  double e = fma(-h, g, 0.5);
-  g = fma(g, e, g);
-  h = fma(h, e, h);
-  e = fma(-h, g, 0.5);
+  const double e = fma(-h, g, 0.5);
   g = fma(g, e, g);
   h = fma(h, e, h);
   g = fma(fma(-g, g, x), h, g);

@@ -457,9 +457,11 @@ class FTLE(LagrangianDiagnostic2D):
     # K1 chunks on alternating streams (chunk c+1 fills the SMs as chunk c drains), K2 on its own
     # high-priority stream; False: everything in order on one stream (K2 between the chunks)
     overlap_chunks = False
-    # K2 of every chunk but the last on the priority stencil stream (runs beside the start of
-    # the next K1 instead of between the two K1 launches)
-    side_stencil = True
+    # K2 of every chunk but the last on the priority stencil stream, enqueued before the next K1.
+    # Measured WORSE at 8 GPUs (9.82 vs 9.05 ms): the next K1's persistent CTAs are dispatched
+    # first, K2 gets no SM slot until that chunk drains, and the copy of the first chunk's rows
+    # starts a chunk late.  Kept as a switch for the record.
+    side_stencil = False
     trace = None  # set to [] to collect (rank, label, timed CUDA event) of the next group call
     # device result: the K2 launches of this many last chunks (and of the rows that wait for a
     # halo exchange) store straight into the other GPUs' fields (dlb_ftle_stencil_gather);
