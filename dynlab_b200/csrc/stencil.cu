@@ -267,10 +267,10 @@ __global__ void __launch_bounds__(TB_THREADS, XI ? DLB_TB_MINB_XI : 8)
   __shared__ __align__(128) double ring[TB_SLOTS][2 * TB_THREADS];
   __shared__ __align__(8) unsigned long long full[TB_SLOTS];
   __shared__ double2 ysm[TB_ROWS][2];
-  __shared__ double2 logtab_s[KIND == KIND_FTLE ? ST_LOGTAB_N : 1];
+  __shared__ double2 logtab_s[KIND == KIND_FTLE ? 128 : 1];
   const long long xdim = P.ax.n, ydim = P.ay.n;
   const int t = threadIdx.x;
-  if (KIND == KIND_FTLE) stage_logtab(logtab_s);
+  if (KIND == KIND_FTLE) logtab_s[t] = g_logtab[t];  // TB_THREADS == 128 entries
   const long long r_lo = (P.out_row0 > 1) ? P.out_row0 : 1;
   const long long r_hi = (P.out_row0 + P.out_rows < ydim - 1) ? P.out_row0 + P.out_rows : ydim - 1;
   const long long ncols_out = xdim - 2;
@@ -418,10 +418,10 @@ __global__ void __launch_bounds__(TM_THREADS, DLB_TM_MINB)
   extern __shared__ __align__(128) unsigned char tiles[];  // [TM_STAGES][TM_STAGE_BYTES]
   __shared__ __align__(8) unsigned long long full[TM_STAGES];
   __shared__ double2 ysm[TM_ROWS][2];
-  __shared__ double2 logtab_s[KIND == KIND_FTLE ? ST_LOGTAB_N : 1];
+  __shared__ double2 logtab_s[KIND == KIND_FTLE ? 128 : 1];
   const long long xdim = P.ax.n, ydim = P.ay.n;
   const int t = threadIdx.x;
-  if (KIND == KIND_FTLE) stage_logtab(logtab_s);
+  if (KIND == KIND_FTLE) logtab_s[t] = g_logtab[t];  // TM_THREADS == 128 entries
   const long long r_lo = (P.out_row0 > 1) ? P.out_row0 : 1;
   const long long r_hi = (P.out_row0 + P.out_rows < ydim - 1) ? P.out_row0 + P.out_rows : ydim - 1;
   const long long ncols_out = xdim - 2;
@@ -609,7 +609,7 @@ int launch_tma_uv(const StencilParams& P, const CUtensorMap& m0, const CUtensorM
   return DLB_OK;
 }
 
-// (fl(1/c), -ln(fl(1/c))) for c = 1 + i/512, uploaded once per device (a __device__ symbol has
+// (fl(1/c), -ln(fl(1/c))) for c = 1 + i/128, uploaded once per device (a __device__ symbol has
 // one instance per device).
 int ensure_logtab() {
   static std::mutex mu;
@@ -618,9 +618,9 @@ int ensure_logtab() {
   int dev = 0;
   DLB_CUDA_CHECK(cudaGetDevice(&dev));
   if (done[dev & (DLB_MAX_DEVICES - 1)]) return DLB_OK;
-  static double2 h[ST_LOGTAB_N];
-  for (int i = 0; i < ST_LOGTAB_N; ++i) {
-    const double c = 1.0 + i / (double)ST_LOGTAB_N;
+  double2 h[128];
+  for (int i = 0; i < 128; ++i) {
+    const double c = 1.0 + i / 128.0;
     const double inv = (i == 0) ? 1.0 : 1.0 / c;
     h[i].x = inv;
     h[i].y = (i == 0) ? 0.0 : (double)(-logl((long double)inv));

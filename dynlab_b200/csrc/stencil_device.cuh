@@ -374,34 +374,26 @@ __device__ __forceinline__ double fast_log_ge1(double x) {
   return hi_part + lo_part;
 }
 
-// Table-driven ln(x), x >= 1 finite: x = 2^e m, m in [1, 2), c = 1 + i / 512 with i the top nine
-// mantissa bits; ln x = e ln2 + ln c + ln1p(r), r = m / c - 1 in [0, 2^-9).  The table holds
+// Table-driven ln(x), x >= 1 finite: x = 2^e m, m in [1, 2), c = 1 + i/128 with i the top seven
+// mantissa bits; ln x = e ln2 + ln c + ln1p(r), r = m / c - 1 in [0, 2^-7).  The table holds
 // (fl(1/c), -ln(fl(1/c))) so that the rounding of 1/c cancels; entry 0 is (1, 0), which keeps
-// full relative accuracy for x -> 1.  ln1p(r) = r + r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6):
-// the first dropped term is r^7 / 7 < 2^-56 r.  11 FP64 instructions (the series version: 27;
-// round 1's 128-entry table: 13) - the FTLE kernel is bound by FP64 instruction issue.
-constexpr int ST_LOGTAB_BITS = 9;
-constexpr int ST_LOGTAB_N = 1 << ST_LOGTAB_BITS;
-__device__ double2 g_logtab[ST_LOGTAB_N];
+// full relative accuracy for x -> 1.  13 FP64 instructions instead of 27 for the series
+// version: the FTLE kernel is co-limited by the FP64 pipe (sqrt + log per point).
+__device__ double2 g_logtab[128];
 
 __device__ __forceinline__ double fast_log_ge1_tab(double x, const double2* tab) {
   const int hi = __double2hiint(x);
   const int e = (hi >> 20) - 1023;
   const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
-  const double2 t = tab[(hi >> (20 - ST_LOGTAB_BITS)) & (ST_LOGTAB_N - 1)];
+  const double2 t = tab[(hi >> 13) & 0x7f];
   const double r = fma(m, t.x, -1.0);
-  double q = ST_LOGK[14];
+  double q = ST_LOGK[12];
 #pragma unroll
-  for (int k = 15; k <= 18; ++k) q = fma(q, r, ST_LOGK[k]);  // -1/6 ... -1/2
+  for (int k = 13; k <= 18; ++k) q = fma(q, r, ST_LOGK[k]);  // -1/8 ... -1/2
   const double ed = (double)e;
   const double hi_part = fma(ed, ST_LOGK[9], t.y);
   const double lo_part = fma(ed, ST_LOGK[10], fma(r * r, q, r));
   return hi_part + lo_part;
-}
-
-// every thread of the CTA helps to stage the table in shared memory
-__device__ __forceinline__ void stage_logtab(double2* dst) {
-  for (int i = threadIdx.x; i < ST_LOGTAB_N; i += blockDim.x) dst[i] = g_logtab[i];
 }
 
 // Per-point epilogue shared by the interior and the edge kernels.
