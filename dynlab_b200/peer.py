@@ -132,6 +132,31 @@ class Group:
         buf = self._sym[key] = SymBuf(int(nbytes), addr, own_tensor, closers)
         return buf
 
+    def release(self) -> None:
+        """Free every symmetric block of this group (collective in the torchrun case).  Tensors
+        that alias them - results of earlier ``compute_device`` calls, ``flow_map`` rows - must
+        not be used afterwards.  Blocks are otherwise kept for the life of the process (per grid
+        shape: three field-sized blocks and two slab-sized flow-map blocks per member), because
+        returned tensors alias them."""
+        for m in self.local:
+            torch.cuda.synchronize(m.device)
+        if self.multiprocess:
+            dist.barrier()  # nobody is still pushing into a block that is about to go
+        for key, buf in list(self._sym.items()):
+            if buf is self.flags:
+                continue
+            for m in self.local:
+                with torch.cuda.device(m.device):
+                    for p in buf._closers:
+                        nat.check(nat.lib.dlb_ipc_close(p))
+                    buf._closers = []
+            if self.multiprocess:
+                dist.barrier()  # every importer has unmapped before the owner frees
+            for m in self.local:
+                with torch.cuda.device(m.device):
+                    nat.check(nat.lib.dlb_peer_free(buf.addr[m.rank][m.rank]))
+            del self._sym[key]
+
     def next_generation(self) -> int:
         self.generation += 1
         return self.generation
@@ -276,6 +301,12 @@ def _single_process_devices(n_seeds):
             raise ValueError(f"{spec} devices requested, {torch.cuda.device_count()} visible")
         return list(range(spec))
     return list(spec)
+
+
+def release_all() -> None:
+    """``Group.release`` for every group of this process."""
+    for g in _groups.values():
+        g.release()
 
 
 def current_group(n_seeds=None):

@@ -1123,6 +1123,13 @@ def test_single_process_group_matches_single_device(dl):
                         fd = d.compute_device(x, y, fl.double_gyre, t, **kw)
                         assert np.array_equal(fd.cpu().numpy(), f1), (nx, ny, halo, weighted, rep)
             peer.current_group(nx * ny).check_timeouts()
+        g = peer.current_group(1 << 30)
+        assert len(g._sym) > 1
+        peer.release_all()  # symmetric blocks are freed; the flags block stays for the next call
+        assert list(g._sym) == [("flags", peer.FLAG_WORDS * 8)]
+        d = D.FTLE()
+        f = np.ma.getdata(d.compute(x, y, fl.double_gyre, t, **kw))
+        assert np.array_equal(f, f1)
     finally:
         peer.set_devices("auto")
         sharding.set_halo_mode("redundant")
