@@ -263,7 +263,7 @@ class Engine:
     # -- K1 ---------------------------------------------------------------------------
     def flow_map(self, flow_id, params, x, y, row0, rows, t0, tf, rtol, atol,
                  max_step=math.inf, first_step=0.0, out=None, nfev=None, status=None,
-                 counters=None, ws_slot=None):
+                 counters=None, ws_slot=None, coords=None):
         """Enqueue K1 for rows [row0, row0+rows) of the grid; returns the [rows, xdim, 2] tensor.
         ``ws_slot``: use that private K1 workspace instead of the engine's shared one (launches
         that run concurrently with other launches of this engine)."""
@@ -276,7 +276,8 @@ class Engine:
             else:
                 ws, wsz = self.k1_workspace(ws_slot, xdim, rows)
             p = nat.darray(params)
-            dx, dy = self.device_coord(x), self.device_coord(y)
+            # coords: (device x, device y) looked up once by a caller that launches many chunks
+            dx, dy = coords if coords is not None else (self.device_coord(x), self.device_coord(y))
             with self._timed("rk45_flowmap"):
               nat.check(nat.lib.dlb_flowmap_rk45_resident(
                 flow_id, p, len(params), dx.data_ptr(), xdim, dy.data_ptr(), row0, rows,

@@ -276,14 +276,14 @@ class LagrangianDiagnostic2D(Diagnostic2D, ABC):
                     max_step=kw["max_step"], first_step=first or 0.0)
 
     def _integrate_rows(self, plan, row0, rows, out, counters=None, eng=None, y=None, nfev=None,
-                        ws_slot=None):
+                        ws_slot=None, coords=None):
         """Enqueue K1 for rows [row0, row0 + rows) of the grid into ``out`` ([rows, xdim, 2])
         on ``eng``'s device (default: the current one)."""
         eng = eng or Engine.get()
         return eng.flow_map(plan["fid"], plan["params"], self._xf, self._yf if y is None else y,
                             row0, rows, plan["t0"], plan["tf"], plan["rtol"], plan["atol"],
                             plan["max_step"], plan["first_step"], out=out, counters=counters,
-                            nfev=nfev, ws_slot=ws_slot)
+                            nfev=nfev, ws_slot=ws_slot, coords=coords)
 
     # -- cost-weighted row slabs ------------------------------------------------------------
     _row_cost_cache: dict = {}

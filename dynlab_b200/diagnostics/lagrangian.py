@@ -248,7 +248,8 @@ class FTLE(LagrangianDiagnostic2D):
                 counters = torch.zeros(max(len(steps), 1), nat.CNT_WORDS, dtype=torch.int64,
                                        device=m.device)
             runs.append(dict(m=m, s=s, steps=steps, tail=tail, fm=fm, out=out, out_row0=out_row0,
-                             counters=counters, main=main, pushes=0))
+                             counters=counters, main=main, pushes=0,
+                             coords=(eng.device_coord(self._xf), eng.device_coord(self._yf))))
 
         trace = self.trace if isinstance(self.trace, list) else None
 
@@ -342,7 +343,8 @@ class FTLE(LagrangianDiagnostic2D):
                     # SMs CTA by CTA as chunk c drains - no tail bubble between chunks
                     self._integrate_rows(plan, r0, r1 - r0, run["fm"][r0 - lo:r1 - lo],
                                          counters=run["counters"][c], eng=m.engine,
-                                         ws_slot=(c % 2) if overlap else None)
+                                         ws_slot=(c % 2) if overlap else None,
+                                         coords=run["coords"])
                     if overlap:
                         ev = torch.cuda.Event()
                         ev.record(k1s)
