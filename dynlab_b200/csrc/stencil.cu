@@ -398,9 +398,6 @@ constexpr int TM_ROWS = TM_LOAD - 2;            // output rows per task (62)
 #endif
 constexpr int TM_STAGES = DLB_TM_STAGES;        // stages in flight
 constexpr int TM_STAGE_BYTES = TM_RT * TM_THREADS * 16;
-#ifndef DLB_WARPSPEC_DEFAULT
-#define DLB_WARPSPEC_DEFAULT 0  // 1: producer-warp flavour of the tile kernel (stencil_tmaw_kernel)
-#endif
 #ifndef DLB_TM_MINB
 #define DLB_TM_MINB 5  // <= 102 registers (the Xi variants want ~90; 6 made them spill: +10 %)
 #endif
@@ -555,186 +552,6 @@ __global__ void __launch_bounds__(TM_THREADS, DLB_TM_MINB)
   }
 }
 
-// ---- warp-specialised flavour of the tile kernel ---------------------------------------------
-// Same tiles, same arithmetic, same results; what changes is who refills the ring.  In
-// stencil_tma_kernel thread 0 re-issues a slot after a CTA-wide __syncthreads per stage, so the
-// four warps of a CTA move in lockstep and ncu's top stall is "barrier" (1.26 / 1.74 per issue
-// for K2 / K3).  Here a fifth warp is the producer: consumers arrive on an `empty` mbarrier per
-// slot when their warp has read it, the producer waits on that and issues the next tile - the
-// canonical full / empty TMA pipeline; consumer warps may run stages apart.
-constexpr int TW_THREADS = TM_THREADS + 32;
-// 5 CTAs of 160 threads leave 80 registers per thread; the variants with the long epilogues
-// (eigenvector, rate / ratio division, peer stores) take 4 CTAs (102 registers) instead of spilling
-constexpr int tw_minb(int kind, int mode, bool xi) {
-  return (xi || (kind == KIND_EULER && mode >= DLB_EULER_RATE) ||
-          (kind == KIND_FTLE && mode == FTLE_PUSH))
-             ? 4
-             : 5;
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void consumer_sync() {  // named barrier 1: the 128 consumer threads
-  asm volatile("bar.sync 1, %0;" ::"n"(TM_THREADS) : "memory");
-}
-
-template <int KIND, int MODE, bool XI, bool AOS, bool UX, bool UY>
-__global__ void __launch_bounds__(TW_THREADS, tw_minb(KIND, MODE, XI))
-    stencil_tmaw_kernel(const StencilParams P, const __grid_constant__ CUtensorMap map0,
-                       const __grid_constant__ CUtensorMap map1) {
-  extern __shared__ __align__(128) unsigned char tiles[];  // [TM_STAGES][TM_STAGE_BYTES]
-  __shared__ __align__(8) unsigned long long full[TM_STAGES];
-  __shared__ __align__(8) unsigned long long empty[TM_STAGES];
-  __shared__ double2 ysm[TM_ROWS][2];
-  __shared__ double2 logtab_s[KIND == KIND_FTLE ? 128 : 1];
-  const long long xdim = P.ax.n, ydim = P.ay.n;
-  const int t = threadIdx.x;
-  if (KIND == KIND_FTLE) logtab_s[t] = g_logtab[t];  // TM_THREADS == 128 entries
-  const long long r_lo = (P.out_row0 > 1) ? P.out_row0 : 1;
-  const long long r_hi = (P.out_row0 + P.out_rows < ydim - 1) ? P.out_row0 + P.out_rows : ydim - 1;
-  const long long ncols_out = xdim - 2;
-  if (r_hi <= r_lo || ncols_out <= 0) return;
-  const long long nstrips = (ncols_out + TM_OUT - 1) / TM_OUT;
-  const long long nchunks = (r_hi - r_lo + TM_ROWS - 1) / TM_ROWS;
-  const long long ntasks = nstrips * nchunks;
-  if ((long long)blockIdx.x >= ntasks) return;
-  const long long my_tasks = (ntasks - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  const long long total_stages = my_tasks * TM_SPT;
-  // np.gradient's uniform / non-uniform branch per axis is a template parameter: as a run-time
-  // flag it cost a predicated copy of both x formulas and a real branch around the y formula
-  // in every row
-  constexpr bool ux = UX, uy = UY;
-  const double ix = P.ax.inv2h, iy = P.ay.inv2h;
-
-  // producer side (thread 0): stage q of this CTA's stream = stage (q % TM_SPT) of its task q / TM_SPT
-  auto issue = [&](long long q) {
-    const long long task = blockIdx.x + (q / TM_SPT) * gridDim.x;
-    const int st = (int)(q % TM_SPT);
-    const long long chunk = task / nstrips, strip = task - chunk * nstrips;
-    const int c0 = (int)(strip * TM_OUT);
-    const int lrow = (int)(r_lo + chunk * TM_ROWS - 1 - P.grow0) + st * TM_RT;
-    const int slot = (int)(q % TM_STAGES);
-    unsigned char* dst = tiles + slot * TM_STAGE_BYTES;
-    mbar_expect_tx(&full[slot], TM_STAGE_BYTES);
-    if (AOS) {
-      tma_load_2d(dst, &map0, 2 * c0, lrow, &full[slot]);
-    } else {
-      tma_load_2d(dst, &map0, c0, lrow, &full[slot]);
-      tma_load_2d(dst + TM_STAGE_BYTES / 2, &map1, c0, lrow, &full[slot]);
-    }
-  };
-  if (t == 0) {
-#pragma unroll
-    for (int i = 0; i < TM_STAGES; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], TM_THREADS / 32);  // one arrival per consumer warp
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (t >= TM_THREADS) {
-    // ---- producer warp: keeps TM_STAGES tile loads in flight; a slot is refilled as soon as
-    // the four consumer warps have released it (no CTA-wide barrier anywhere in the stream)
-    if (t == TM_THREADS) {
-      for (long long q = 0; q < total_stages; ++q) {
-        if (q >= TM_STAGES) {
-          const int slot = (int)(q % TM_STAGES);
-          const unsigned parity = (unsigned)(((q / TM_STAGES) - 1) & 1);
-          while (!mbar_try_wait(&empty[slot], parity)) {
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
-        issue(q);
-      }
-    }
-    return;
-  }
-
-  long long q = 0;  // stages consumed so far (CTA-uniform)
-  for (long long it = 0; it < my_tasks; ++it) {
-    const long long task = blockIdx.x + it * gridDim.x;
-    const long long chunk = task / nstrips, strip = task - chunk * nstrips;
-    const long long c0 = strip * TM_OUT;
-    const long long g0 = r_lo + chunk * TM_ROWS;  // first output row of the task
-    const int nrows = (int)((g0 + TM_ROWS < r_hi) ? TM_ROWS : r_hi - g0);
-    const long long col = (c0 + t < xdim) ? c0 + t : xdim - 1;
-    const bool emit_thread = (t >= 1) && (t <= TM_OUT) && (c0 + t <= xdim - 2);
-    const int tl = (t > 0) ? t - 1 : 0, tr = (t < TM_THREADS - 1) ? t + 1 : TM_THREADS - 1;
-    double xa = 0.0, xb = 0.0, xc = 0.0;
-    if (!ux) {
-      xa = __ldg(P.ax.ca + col);
-      xb = __ldg(P.ax.cb + col);
-      xc = __ldg(P.ax.cc + col);
-    }
-    if (!uy) {
-      consumer_sync();  // the previous task's readers of ysm are done
-      if (t < nrows) {
-        const double2* src = P.ay4 + 2 * (g0 + t);
-        ysm[t][0] = __ldg(src);
-        ysm[t][1] = __ldg(src + 1);
-      }
-      consumer_sync();
-    }
-    // loaded row r of the task is global row g0 - 1 + r; while row r streams in as D, the centre
-    // row r - 1 (registers C, L, R) with U = row r - 2 is emitted: output row index k = r - 2
-    double2 U = make_double2(0.0, 0.0), C = U, L = U, R = U;
-    long long o = (g0 - 2 - P.out_row0) * xdim + col;  // output offset of k = -2 (never stored)
-#pragma unroll 1
-    for (int st = 0; st < TM_SPT; ++st, ++q) {
-      const int slot = (int)(q % TM_STAGES);
-      const unsigned parity = (unsigned)((q / TM_STAGES) & 1);
-      while (!mbar_try_wait(&full[slot], parity)) {
-      }
-      const unsigned char* tile = tiles + slot * TM_STAGE_BYTES;
-#pragma unroll
-      for (int j = 0; j < TM_RT; ++j) {
-        double2 D, Ld, Rd;
-        if (AOS) {
-          const double2* row = reinterpret_cast<const double2*>(tile) + j * TM_THREADS;
-          D = row[t];
-          Ld = row[tl];
-          Rd = row[tr];
-        } else {
-          const double* ru = reinterpret_cast<const double*>(tile) + j * TM_THREADS;
-          const double* rv = ru + TM_RT * TM_THREADS;
-          D = make_double2(ru[t], rv[t]);
-          Ld = make_double2(ru[tl], rv[tl]);
-          Rd = make_double2(ru[tr], rv[tr]);
-        }
-        const int k = st * TM_RT + j - 2;  // output row of the centre held in C
-        double d0dx, d1dx, d0dy, d1dy;
-        if (ux) {
-          d0dx = (R.x - L.x) * ix;
-          d1dx = (R.y - L.y) * ix;
-        } else {
-          d0dx = fma(xc, R.x, fma(xb, C.x, xa * L.x));
-          d1dx = fma(xc, R.y, fma(xb, C.y, xa * L.y));
-        }
-        if (uy) {
-          d0dy = (D.x - U.x) * iy;
-          d1dy = (D.y - U.y) * iy;
-        } else {
-          const int kc = (k < 0) ? 0 : k;
-          const double2 yab = ysm[kc][0], ycz = ysm[kc][1];
-          d0dy = fma(ycz.x, D.x, fma(yab.y, C.x, yab.x * U.x));
-          d1dy = fma(ycz.x, D.y, fma(yab.y, C.y, yab.x * U.y));
-        }
-        emit_pred<KIND, MODE, XI>(P, C, d0dx, d1dx, d0dy, d1dy, o,
-                                  KIND == KIND_FTLE ? logtab_s : nullptr,
-                                  emit_thread && k >= 0 && k < nrows);
-        o += xdim;
-        U = C;
-        C = D;
-        L = Ld;
-        R = Rd;
-      }
-      // this warp has read the stage: release its share of the slot to the producer warp
-      __syncwarp();
-      if ((t & 31) == 0) mbar_arrive(&empty[slot]);
-    }
-  }
-}
-
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -772,31 +589,8 @@ bool make_tile_map(CUtensorMap* map, const void* base, long long inner, long lon
 }
 
 template <int KIND, int MODE, bool XI, bool AOS, bool UX, bool UY>
-int launch_tmaw_uv(const StencilParams& P, const CUtensorMap& m0, const CUtensorMap& m1,
-                   long long ntasks, cudaStream_t stream) {
-  auto kern = stencil_tmaw_kernel<KIND, MODE, XI, AOS, UX, UY>;
-  constexpr int dyn = TM_STAGES * TM_STAGE_BYTES;
-  static int per_sm_of[DLB_MAX_DEVICES] = {0};
-  int dev = 0;
-  DLB_CUDA_CHECK(cudaGetDevice(&dev));
-  int& per_sm = per_sm_of[dev & (DLB_MAX_DEVICES - 1)];
-  if (per_sm == 0) {
-    DLB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-    DLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TW_THREADS, dyn));
-    if (per_sm < 1) per_sm = 1;
-  }
-  long long blocks = (long long)num_sms() * per_sm;
-  if (blocks > ntasks) blocks = ntasks;
-  kern<<<(unsigned)blocks, TW_THREADS, dyn, stream>>>(P, m0, m1);
-  DLB_CUDA_CHECK(cudaGetLastError());
-  return DLB_OK;
-}
-
-template <int KIND, int MODE, bool XI, bool AOS, bool UX, bool UY>
 int launch_tma_uv(const StencilParams& P, const CUtensorMap& m0, const CUtensorMap& m1,
                   long long ntasks, cudaStream_t stream) {
-  if (env_flag("DLB_STENCIL_WARPSPEC", DLB_WARPSPEC_DEFAULT))
-    return launch_tmaw_uv<KIND, MODE, XI, AOS, UX, UY>(P, m0, m1, ntasks, stream);
   auto kern = stencil_tma_kernel<KIND, MODE, XI, AOS, UX, UY>;
   constexpr int dyn = TM_STAGES * TM_STAGE_BYTES;
   static int per_sm_of[DLB_MAX_DEVICES] = {0};  // the attribute is a per-device setting
