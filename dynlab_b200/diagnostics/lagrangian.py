@@ -217,9 +217,8 @@ class FTLE(LagrangianDiagnostic2D):
             ring = [G.symmetric(("field", k), ydim * xdim * 8) for k in range(peer.RESULT_DEPTH)]
             field_sym = ring[gen % peer.RESULT_DEPTH]
         elif G.multiprocess:
-            ring = [sharding.shared_host_array((ydim, xdim), tag=("result", k))
-                    for k in range(peer.RESULT_DEPTH)]
-            host_np, host_t = ring[gen % peer.RESULT_DEPTH]
+            # a shared host segment no rank still holds a result in (SharedResultPool)
+            host_np, host_t = sharding.SharedResultPool.get((ydim, xdim)).acquire()
         else:
             host_t = torch.empty((ydim, xdim), dtype=torch.float64, pin_memory=True)
             host_np = host_t.numpy()

@@ -87,13 +87,13 @@ _host_result = "shared"  # how the ranks of a torchrun job receive the field in 
 def set_host_result(which) -> None:
     """One process per GPU: how every rank's ``FTLE.compute`` gets the full host field.
     ``"shared"`` (default): the ranks of the box share pinned host segments
-    (``shared_host_array``); each rank streams only its own rows into the segment while it is
+    (``SharedResultPool``); each rank streams only its own rows into the segment while it is
     still integrating and every rank returns a view of the whole, so the field crosses PCIe once
-    instead of once per rank and nothing is gathered on the devices.  The segments rotate
-    (``peer.RESULT_DEPTH`` = 3 per grid shape): a returned array keeps its values through the
-    next ``compute`` of that shape and is overwritten by the one after; it is the same memory on
-    every rank.  ``"private"``: each rank returns its own ordinary numpy copy (costs a
-    ydim*xdim*8-byte host memcpy per rank per call)."""
+    instead of once per rank and nothing is gathered on the devices.  A segment is only handed
+    out again when no rank holds a result (or a view of one) in it any more, so results behave
+    like the reference's freshly allocated arrays - except that the memory is the same on every
+    rank (write into it and the other ranks see it).  ``"private"``: each rank returns its own
+    ordinary numpy copy (costs a ydim*xdim*8-byte host memcpy per rank per call)."""
     global _host_result
     if which == "all":  # round-1 name of the private-copy mode
         which = "private"
@@ -173,6 +173,69 @@ def shared_host_array(shape, dtype=np.float64, tag="result"):
         seg = _segments[key] = (mm, flat)
     arr = seg[1][:nbytes].view(dtype).reshape(shape)
     return arr, torch.from_numpy(arr)
+
+
+class SharedResultPool:
+    """Shared host segments for the results of one grid shape, handed out so that a result
+    array the caller still holds on ANY rank is never overwritten.
+
+    Every ``acquire`` wraps the chosen segment in a fresh ``np.frombuffer`` owner array; numpy
+    makes every view derived from the returned result (``field[10:20]``, ``field.T``, the masked
+    array's data) keep that owner alive, so a weak reference to it says exactly whether anything
+    still looks at the segment.  The ranks exchange their busy bits through shared memory (two
+    host barriers, ~20 us) and all pick the first segment free everywhere; if there is none a
+    new one is created (collective, ~0.1 s: only when the caller accumulates results).  A plain
+    ``f = d.compute(...)`` loop alternates between two segments."""
+
+    _pools: dict = {}
+
+    @classmethod
+    def get(cls, shape, dtype=np.float64) -> "SharedResultPool":
+        key = (tuple(int(v) for v in shape), np.dtype(dtype).str)
+        pool = cls._pools.get(key)
+        if pool is None:
+            pool = cls._pools[key] = SharedResultPool(*key)
+        return pool
+
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = shape, np.dtype(dtype)
+        self.owners = []  # per segment: weakref to the owner array of its last hand-out (or None)
+        self.calls = 0
+
+    def _busy_bits(self) -> int:
+        bits = 0
+        for k, ref in enumerate(self.owners):
+            if ref is not None and ref() is not None:
+                bits |= 1 << k
+        return bits
+
+    def acquire(self):
+        """Collective.  Returns ``(numpy array, torch tensor)`` over a segment no rank still
+        uses; both alias the same page-locked shared memory."""
+        import weakref
+
+        rank, size = world()
+        board, _ = shared_host_array((max(size, 8),), dtype=np.int64, tag="result-pool-board")
+        board[rank] = self._busy_bits()
+        host_barrier()
+        busy = 0
+        for r in range(size):
+            busy |= int(board[r])
+        host_barrier()  # everybody has read the board before anybody writes it again
+        k = 0
+        while k < len(self.owners) and (busy >> k) & 1:
+            k += 1
+        if k == len(self.owners):
+            self.owners.append(None)
+        # cached by (tag, nbytes): created on first use of index k, collectively
+        _, _ = shared_host_array(self.shape, self.dtype, tag=("result", self.shape, k))
+        mm, flat = _segments[(("result", self.shape, k), int(np.prod(self.shape)) * self.dtype.itemsize)]
+        n = int(np.prod(self.shape))
+        owner = np.frombuffer(mm, dtype=self.dtype, count=n)  # fresh object: the liveness token
+        self.owners[k] = weakref.ref(owner)
+        self.calls += 1
+        arr = owner.reshape(self.shape)
+        return arr, torch.from_numpy(arr)
 
 
 def world():

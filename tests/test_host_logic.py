@@ -310,6 +310,31 @@ def _shared_worker(rank, size, port, out_dir):
             sharding.host_barrier()
             assert (stamp >= gen + 1).all()
             sharding.host_barrier()
+        # SharedResultPool: a segment is handed out again only when NO rank holds a result in it
+        pool = sharding.SharedResultPool.get((5, 4))
+        r1, _ = pool.acquire()
+        r1[:] = 1.0
+        view = r1[1:3]                      # a derived view keeps the segment busy too
+        r2, _ = pool.acquire()
+        r2[:] = 2.0
+        assert (r1 == 1.0).all() and len(pool.owners) == 2
+        del r1
+        r3, _ = pool.acquire()              # r1's segment is still seen through `view`
+        r3[:] = 3.0
+        assert (view == 1.0).all() and (r2 == 2.0).all() and len(pool.owners) == 3
+        del view
+        if rank != 0:
+            del r2                          # rank 0 keeps r2: busy for everybody
+        r4, _ = pool.acquire()              # -> the segment r1 / view lived in
+        r4[:] = 4.0
+        assert len(pool.owners) == 3 and (r3 == 3.0).all()
+        dist.barrier()
+        if rank == 0:
+            assert (r2 == 2.0).all()
+        dist.barrier()
+        del r3, r4
+        if rank == 0:
+            del r2
         n_before = len(sharding._segments)
         other, _ = sharding.shared_host_array((3, 5))
         assert other.shape == (3, 5) and len(sharding._segments) == n_before + 1
