@@ -205,10 +205,7 @@ class EulerianDiagnostic2D(Diagnostic2D, ABC):
                                          negate, xi_mode)
 
         def gather(part, tail, dtype):
-            pad = torch.zeros((slab.rows_max, self.xdim) + tail, dtype=dtype, device=eng.device)
-            if part is not None:
-                pad[:slab.rows] = part
-            return sharding.gather_rows(pad, self.ydim, size)
+            return sharding.gather_slab(part, slab, self.ydim, (self.xdim,) + tail, dtype, eng.device)
 
         need_mask = mode in (nat.EULER_RATE, nat.EULER_RATIO)
         return (gather(f, (), torch.float64),

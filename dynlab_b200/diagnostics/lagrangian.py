@@ -29,17 +29,13 @@ def _ftle_on_device(diag, local, slab, t, edge_order, xi_mode):
     if size == 1:
         return eng.ftle_stencil(local, 0, diag._xf, diag._yf, edge_order, t_span, 0, diag.ydim,
                                 xi_mode)
-    out = torch.empty(slab.rows_max, diag.xdim, dtype=torch.float64, device=eng.device)
-    xi = None
+    out = xi = None
     if slab.rows:
-        _, xi = eng.ftle_stencil(local, slab.lo, diag._xf, diag._yf, edge_order, t_span,
-                                 slab.row0, slab.rows, xi_mode, out=out[:slab.rows])
-    field = sharding.gather_rows(out, diag.ydim, size)
+        out, xi = eng.ftle_stencil(local, slab.lo, diag._xf, diag._yf, edge_order, t_span,
+                                   slab.row0, slab.rows, xi_mode)
+    field = sharding.gather_slab(out, slab, diag.ydim, (diag.xdim,), torch.float64, eng.device)
     if xi_mode != nat.XI_NONE:
-        pad = torch.empty(slab.rows_max, diag.xdim, 2, dtype=torch.float64, device=eng.device)
-        if xi is not None:
-            pad[:slab.rows] = xi
-        xi = sharding.gather_rows(pad, diag.ydim, size)
+        xi = sharding.gather_slab(xi, slab, diag.ydim, (diag.xdim, 2), torch.float64, eng.device)
     return field, xi
 
 

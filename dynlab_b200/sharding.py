@@ -347,6 +347,41 @@ def exchange_halo(local: torch.Tensor, slab: Slab, ydim: int, rank: int, size: i
         req.wait()
 
 
+def gather_slab(part, slab: "Slab", ydim: int, tail, dtype, device) -> torch.Tensor:
+    """Rows [slab.row0, +slab.rows) of a ``[ydim, *tail]`` array live on this rank (``part``,
+    None for an idle rank); returns the whole array on every rank.  The uniform ``partition``
+    is assumed.  CUDA tensors with the ``"peer"`` transport: the rows are pushed into every
+    rank's copy over NVLink peer memory (``dlb_gather_rows`` + ``dlb_wait_flags``, csrc/peer.cu;
+    the result lives in one of ``peer.RESULT_DEPTH`` rotating symmetric buffers).  Otherwise
+    (``"nccl"`` transport, CPU tensors under gloo): padded all-gather through torch.distributed."""
+    rank, size = world()
+    tail = tuple(int(v) for v in tail)
+    if torch.device(device).type == "cuda" and _transport == "peer":
+        from . import peer
+
+        G = peer.current_group()
+        (m,) = G.local
+        gen = G.next_generation()
+        item = torch.empty((), dtype=dtype).element_size()
+        row_b = int(np.prod(tail, dtype=np.int64)) * item if tail else item
+        nbytes = ydim * row_b
+        ring = [G.symmetric(("gather", str(dtype), tail, k), nbytes) for k in range(peer.RESULT_DEPTH)]
+        buf = ring[gen % peer.RESULT_DEPTH]
+        full = buf.view(m, dtype, (ydim,) + tail)
+        with torch.cuda.device(m.device):
+            main = torch.cuda.current_stream(m.device)
+            if slab.rows:
+                full[slab.row0:slab.row0 + slab.rows].copy_(part[:slab.rows])
+            G.push_rows(m, buf, slab.row0 * row_b if slab.rows else 0, slab.rows * row_b,
+                        gen * peer.GEN_STRIDE + peer.DONE, main.cuda_stream)
+            G.wait_gathered(m, gen, main.cuda_stream)
+        return full
+    pad = torch.zeros((slab.rows_max,) + tail, dtype=dtype, device=device)
+    if part is not None and slab.rows:
+        pad[:slab.rows] = part[:slab.rows]
+    return gather_rows(pad, ydim, size)
+
+
 def gather_rows(own_padded: torch.Tensor, ydim: int, size: int) -> torch.Tensor:
     """All-gather per-rank outputs (``[rows_max, ...]``, first ``rows`` valid) into the full
     ``[ydim, ...]`` array on every rank."""

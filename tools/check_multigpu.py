@@ -100,28 +100,34 @@ for (nx, ny, eo, t) in grids:
     sharding.set_halo_mode("redundant")
     g = peer.current_group(nx * ny)
     g.check_timeouts()
-    # ---- LCS / Eulerian (NCCL gather path; needs distinct devices)
+    # ---- LCS / Eulerian: uniform slabs, gathered over peer memory (sharding.gather_slab) or NCCL
     if args.backend == "nccl" and nx * ny < 1 << 22:
-        lc = LCS()
-        lc.compute(x, y, f=double_gyre, t=t, percentile=70, debug=True, **kw)
-        xi_sh = np.ma.getdata(lc.Xi_max).copy()
-        a_sh = np.ma.getdata(AttractionRate().compute(x * 1e4, y * 8e3 - 4e3, f=bickley_jet, t=0.1, edge_order=eo)).copy()
         u, v = bickley_jet(0.1, np.meshgrid(x * 1e4, y * 8e3 - 4e3))
-        a_uv = np.ma.getdata(AttractionRate().compute(x * 1e4, y * 8e3 - 4e3, u=u, v=v, edge_order=eo)).copy()
-        r = TrajectoryRepulsionRate().compute(x, y, f=double_gyre, t=0.3, edge_order=eo)
-        r_sh, rm_sh = np.ma.getdata(r).copy(), np.ma.getmaskarray(r).copy()
         sharding.set_distributed(False)
         l1 = LCS()
         l1.compute(x, y, f=double_gyre, t=t, percentile=70, debug=True, **kw)
         a_1 = np.ma.getdata(AttractionRate().compute(x * 1e4, y * 8e3 - 4e3, f=bickley_jet, t=0.1, edge_order=eo))
         a_uv1 = np.ma.getdata(AttractionRate().compute(x * 1e4, y * 8e3 - 4e3, u=u, v=v, edge_order=eo))
-        r = TrajectoryRepulsionRate().compute(x, y, f=double_gyre, t=0.3, edge_order=eo)
+        r1 = TrajectoryRepulsionRate().compute(x, y, f=double_gyre, t=0.3, edge_order=eo)
         sharding.set_distributed(True)
-        results["lcs/xi"] = np.array_equal(xi_sh, np.ma.getdata(l1.Xi_max))
-        results["lcs/lines"] = len(lc.lcs) == len(l1.lcs) and all(np.array_equal(a, b) for a, b in zip(lc.lcs, l1.lcs))
-        results["attraction/flow"] = np.array_equal(a_sh, a_1)
-        results["attraction/uv"] = np.array_equal(a_uv, a_uv1)
-        results["rate"] = np.array_equal(r_sh, np.ma.getdata(r)) and np.array_equal(rm_sh, np.ma.getmaskarray(r))
+        for tr in transports:
+            sharding.set_transport(tr)
+            for rep in range(2):  # twice: rotating gather buffers
+                lc = LCS()
+                lc.compute(x, y, f=double_gyre, t=t, percentile=70, debug=True, **kw)
+                a_sh = np.ma.getdata(AttractionRate().compute(x * 1e4, y * 8e3 - 4e3, f=bickley_jet, t=0.1, edge_order=eo))
+                a_uv = np.ma.getdata(AttractionRate().compute(x * 1e4, y * 8e3 - 4e3, u=u, v=v, edge_order=eo))
+                r = TrajectoryRepulsionRate().compute(x, y, f=double_gyre, t=0.3, edge_order=eo)
+                results[f"{tr}/lcs/xi{rep}"] = np.array_equal(np.ma.getdata(lc.Xi_max), np.ma.getdata(l1.Xi_max))
+                results[f"{tr}/lcs/ftle{rep}"] = np.array_equal(np.ma.getdata(lc.ftle), np.ma.getdata(l1.ftle))
+                results[f"{tr}/lcs/lines{rep}"] = len(lc.lcs) == len(l1.lcs) and all(
+                    np.array_equal(p, q) for p, q in zip(lc.lcs, l1.lcs))
+                results[f"{tr}/attraction/flow{rep}"] = np.array_equal(a_sh, a_1)
+                results[f"{tr}/attraction/uv{rep}"] = np.array_equal(a_uv, a_uv1)
+                results[f"{tr}/rate{rep}"] = (np.array_equal(np.ma.getdata(r), np.ma.getdata(r1))
+                                             and np.array_equal(np.ma.getmaskarray(r), np.ma.getmaskarray(r1)))
+        sharding.set_transport("peer")
+        g.check_timeouts()
     extra = ""
     if args.full and nx == 8192:  # the C oracle on the every-64th sample (bench.py's result_check)
         from oracle import c_oracle as co
