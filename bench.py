@@ -572,6 +572,8 @@ def run_ours(args):
                 single["equals_value_field"] = (single["field_sha256_device"] == value_sha
                                                 and single["field_sha256_host"] == value_sha)
                 del d1, fdev, fh
+            except Exception as exc:  # noqa: BLE001 - a side leg must not take the bench line down
+                single = {"error": repr(exc)}
             finally:
                 peer.set_devices("auto")
                 sharding.set_distributed(True)
@@ -585,7 +587,10 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     configs = None
     if not args.no_configs:
-        configs = extra_configs(eng, hbm_peak, world, rank, quick=world > 1)
+        try:
+            configs = extra_configs(eng, hbm_peak, world, rank, quick=world > 1)
+        except Exception as exc:  # noqa: BLE001 - side legs must not take the bench line down
+            configs = {"error": repr(exc)}
         barrier()
 
     if rank == 0:
