@@ -385,6 +385,43 @@ def test_sharding_mode_switches_validate():
         sharding.set_transport("mpi")
 
 
+def test_single_process_device_selection(monkeypatch):
+    """peer.set_devices / the automatic choice of a plain process (no kernel launches): explicit
+    lists are taken as they are, "auto" shards large grids over every visible device and never
+    inside a torchrun rank, bad specs raise."""
+    from dynlab_b200 import peer
+
+    try:
+        monkeypatch.setattr(peer.torch.cuda, "device_count", lambda: 8)
+        monkeypatch.delenv("WORLD_SIZE", raising=False)
+        peer.set_devices("auto")
+        assert peer._single_process_devices(peer.AUTO_MIN_SEEDS) == list(range(8))
+        assert peer._single_process_devices(peer.AUTO_MIN_SEEDS - 1) is None
+        assert peer._single_process_devices(None) is None
+        monkeypatch.setenv("WORLD_SIZE", "8")     # a torchrun rank owns one device
+        assert peer._single_process_devices(1 << 30) is None
+        monkeypatch.delenv("WORLD_SIZE")
+        peer.set_devices("all")
+        assert peer._single_process_devices(4) == list(range(8))
+        peer.set_devices(3)
+        assert peer._single_process_devices(4) == [0, 1, 2]
+        peer.set_devices([0, 0, 2])
+        assert peer._single_process_devices(4) == [0, 0, 2]
+        peer.set_devices(None)
+        assert peer.devices_spec() == 1 and peer._single_process_devices(1 << 30) is None
+        peer.set_devices(9)
+        with pytest.raises(ValueError):
+            peer._single_process_devices(4)
+        for bad in (0, []):
+            with pytest.raises(ValueError):
+                peer.set_devices(bad)
+        monkeypatch.setattr(peer.torch.cuda, "device_count", lambda: 1)
+        peer.set_devices("auto")
+        assert peer._single_process_devices(1 << 30) is None
+    finally:
+        peer.set_devices("auto")
+
+
 def test_weighted_bounds():
     """Cost-weighted slabs: cover the grid, keep >= 2 rows per active rank, equalise the cost,
     reduce to the uniform partition for a flat cost, and agree with `partition` through
