@@ -53,6 +53,7 @@ class Engine:
         # chunk pipeline of the Lagrangian path: K1 chunks alternate between the caller's stream
         # and `alt_stream` (chunk c+1 fills the SMs as chunk c drains), K2 of a finished chunk
         # runs on the high-priority `stencil_stream` as soon as CTA slots free up
+        self.push_streams = []  # extra copy streams: peer pushes to several GPUs side by side
         self.alt_stream = torch.cuda.Stream(device=self.device)
         self.stencil_stream = torch.cuda.Stream(device=self.device, priority=-1)
         self._k1_ws = {}      # slot -> private K1 workspace (work counter + x, y rows)
@@ -92,6 +93,11 @@ class Engine:
             grown = torch.empty(max(need, 1 << 22), dtype=torch.uint8, device=self.device)
             self._workspace = grown
         return self._workspace.data_ptr(), self._workspace.numel()
+
+    def get_push_streams(self, n: int):
+        while len(self.push_streams) < n:
+            self.push_streams.append(torch.cuda.Stream(device=self.device))
+        return self.push_streams[:n]
 
     def k1_workspace(self, slot: int, xdim: int, rows: int):
         """Private workspace of K1 launches that may overlap other launches (chunk pipeline)."""

@@ -268,9 +268,20 @@ class FTLE(LagrangianDiagnostic2D):
                 ev.record(after or run["main"])
                 eng.copy_stream.wait_event(ev)
                 if target == "device":
-                    G.push_rows(m, field_sym, a * xdim * 8, (b - a) * xdim * 8,
-                                gen * peer.GEN_STRIDE + peer.DONE if last else None,
-                                eng.copy_stream.cuda_stream, dests)
+                    lanes = int(self.push_lanes)
+                    everyone = list(range(G.size)) if dests is None else list(dests)
+                    if lanes > 1 and not last and len(everyone) > 2:
+                        # peers dealt over several copy streams: one engine does not fill the
+                        # NVLink ports of seven receivers
+                        for k, st in enumerate(eng.get_push_streams(lanes)):
+                            st.wait_event(ev)
+                            G.push_rows(m, field_sym, a * xdim * 8, (b - a) * xdim * 8, None,
+                                        st.cuda_stream, everyone[k::lanes])
+                            eng.copy_stream.wait_stream(st)
+                    else:
+                        G.push_rows(m, field_sym, a * xdim * 8, (b - a) * xdim * 8,
+                                    gen * peer.GEN_STRIDE + peer.DONE if last else None,
+                                    eng.copy_stream.cuda_stream, dests)
                     run["pushed"] = torch.cuda.Event()
                     run["pushed"].record(eng.copy_stream)
                     mark(run, f"dma-push rows {a}:{b} done", eng.copy_stream)
@@ -464,6 +475,7 @@ class FTLE(LagrangianDiagnostic2D):
     # halo exchange) store straight into the other GPUs' fields (dlb_ftle_stencil_gather);
     # earlier chunks are pushed by a copy engine behind the integrator
     fused_gather_chunks = 1
+    push_lanes = 1  # copy streams the peer pushes of a chunk are dealt over (device result)
     # device result on several GPUs: chunk sizes (fractions of a slab's rows).  One large chunk
     # whose rows a copy engine spreads while the small last one integrates; the last one's K2 is
     # the fused gather.  (The host result keeps `pipeline_chunks`: equal chunks, because there

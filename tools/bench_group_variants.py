@@ -37,7 +37,7 @@ eng = Engine.get()
 
 
 def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=True, overlap=None,
-        fused=1, hchunks=4, side=True):
+        fused=1, hchunks=4, side=False, lanes=1):
     if args.only and args.only not in name:
         return
     sharding.set_transport(transport)
@@ -49,6 +49,7 @@ def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=Tru
         d.overlap_chunks = overlap
     d.fused_gather_chunks = fused
     d.side_stencil = side
+    d.push_lanes = lanes
     for _ in range(3):
         d.compute_device(x, y, double_gyre, (10, 0), **kw)
     dist.barrier()
@@ -70,7 +71,7 @@ def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=Tru
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     out = {"variant": name, "transport": transport, "halo": halo, "chunks": list(chunks) if isinstance(chunks, tuple) else chunks, "last_fraction": frac,
-           "weighted": weighted, "overlap": overlap, "fused": fused, "side": side, "host_chunks": list(hchunks) if isinstance(hchunks, tuple) else hchunks, "ms_per_step": float(tmax[0]),
+           "weighted": weighted, "overlap": overlap, "fused": fused, "side": side, "push_lanes": lanes, "host_chunks": list(hchunks) if isinstance(hchunks, tuple) else hchunks, "ms_per_step": float(tmax[0]),
            "k1_ms_max_rank": float(tmax[1]), "k1_ms_min_rank": float(tmin[1]),
            "sha": hashlib.sha256(f.cpu().numpy().tobytes()).hexdigest()[:16]}
     if args.trace and transport == "peer":
@@ -108,14 +109,13 @@ def run(name, transport="peer", halo="exchange", chunks=4, frac=32, weighted=Tru
 
 
 run("nccl after the kernels (round 1)", transport="nccl")
-run("default (2 chunks .875/.125, redundant, side stencil)", chunks=(0.875, 0.125), halo="redundant")
-run("default, K2 between the K1 launches", chunks=(0.875, 0.125), halo="redundant", side=False)
-run("default, exchange halo", chunks=(0.875, 0.125), halo="exchange")
-run("2 chunks .9/.1", chunks=(0.9, 0.1), halo="redundant")
-run("3 chunks .5/.4/.1", chunks=(0.5, 0.4, 0.1), halo="redundant")
-run("host chunks 3", hchunks=3, halo="redundant")
-run("host chunks 4", hchunks=4, halo="redundant")
-run("host chunks 4, K2 between", hchunks=4, halo="redundant", side=False)
-run("host chunks (.4,.3,.2,.1)", hchunks=(0.4, 0.3, 0.2, 0.1), halo="redundant")
-run("host chunks (.35,.3,.25,.07,.03)", hchunks=(0.35, 0.3, 0.25, 0.07, 0.03), halo="redundant")
+run("default (.875/.125, 1 push lane)", chunks=(0.875, 0.125), halo="redundant", side=False)
+run(".875/.125, 2 push lanes", chunks=(0.875, 0.125), halo="redundant", side=False, lanes=2)
+run(".875/.125, 4 push lanes", chunks=(0.875, 0.125), halo="redundant", side=False, lanes=4)
+run(".875/.125, 7 push lanes", chunks=(0.875, 0.125), halo="redundant", side=False, lanes=7)
+run(".9375/.0625, 1 push lane", chunks=(0.9375, 0.0625), halo="redundant", side=False)
+run(".9375/.0625, 4 push lanes", chunks=(0.9375, 0.0625), halo="redundant", side=False, lanes=4)
+run(".9375/.0625, 7 push lanes", chunks=(0.9375, 0.0625), halo="redundant", side=False, lanes=7)
+run(".92/.08, 4 push lanes", chunks=(0.92, 0.08), halo="redundant", side=False, lanes=4)
+run(".9/.1, 4 push lanes", chunks=(0.9, 0.1), halo="redundant", side=False, lanes=4)
 dist.destroy_process_group()
