@@ -475,7 +475,10 @@ class FTLE(LagrangianDiagnostic2D):
     # halo exchange) store straight into the other GPUs' fields (dlb_ftle_stencil_gather);
     # earlier chunks are pushed by a copy engine behind the integrator
     fused_gather_chunks = 1
-    push_lanes = 1  # copy streams the peer pushes of a chunk are dealt over (device result)
+    # copy streams the peer pushes of a chunk are dealt over (device result): one per receiver at
+    # 8 GPUs - a single stream's back-to-back copies finished just after the last K1 chunk and
+    # held up the final fused K2 (8.784 -> 8.740 ms, profiles/r02_variants_n8_push_lanes.jsonl)
+    push_lanes = 7
     # device result on several GPUs: chunk sizes (fractions of a slab's rows).  One large chunk
     # whose rows a copy engine spreads while the small last one integrates; the last one's K2 is
     # the fused gather.  (The host result keeps `pipeline_chunks`: equal chunks, because there
