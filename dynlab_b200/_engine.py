@@ -269,10 +269,11 @@ class Engine:
     # -- K1 ---------------------------------------------------------------------------
     def flow_map(self, flow_id, params, x, y, row0, rows, t0, tf, rtol, atol,
                  max_step=math.inf, first_step=0.0, out=None, nfev=None, status=None,
-                 counters=None, ws_slot=None, coords=None):
+                 counters=None, ws_slot=None, coords=None, stat_rows=None):
         """Enqueue K1 for rows [row0, row0+rows) of the grid; returns the [rows, xdim, 2] tensor.
         ``ws_slot``: use that private K1 workspace instead of the engine's shared one (launches
-        that run concurrently with other launches of this engine)."""
+        that run concurrently with other launches of this engine).  ``stat_rows = (row0, rows)``:
+        only those rows enter the counters (default: all integrated rows)."""
         xdim = len(x)
         with torch.cuda.device(self.device):
             if out is None:
@@ -290,8 +291,9 @@ class Engine:
                 float(t0), float(tf), float(rtol), float(atol), float(max_step), float(first_step),
                 out.data_ptr(), nfev.data_ptr() if nfev is not None else None,
                 status.data_ptr() if status is not None else None,
-                (self.counters if counters is None else counters).data_ptr(), ws, wsz,
-                self.stream()))
+                (self.counters if counters is None else counters).data_ptr(),
+                row0 if stat_rows is None else int(stat_rows[0]),
+                rows if stat_rows is None else int(stat_rows[1]), ws, wsz, self.stream()))
         return out
 
     def rk45_endpoints(self, flow_id, params, seeds, t0, tf, rtol, atol, max_step=math.inf,

@@ -32,7 +32,7 @@ SIGNATURES = {
     "dlb_flowmap_rk45": (_i, [_i, _dp, _i, _dp, _i64, _dp, _i64, _i64, _d, _d, _d, _d, _d, _d,
                               _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dlb_flowmap_rk45_resident": (_i, [_i, _dp, _i, _vp, _i64, _vp, _i64, _i64, _d, _d, _d, _d, _d,
-                                       _d, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+                                       _d, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz, _vp]),
     "dlb_rk45_endpoints": (_i, [_i, _dp, _i, _i, _vp, _i64, _d, _d, _d, _dp, _d, _d, _vp, _vp,
                                 _vp, _vp, _vp, _sz, _vp]),
     "dlb_ftle_stencil": (_i, [_vp, _i64, _i64, _dp, _i64, _dp, _i64, _i, _d, _i64, _i64, _vp, _vp,

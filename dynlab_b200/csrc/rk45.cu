@@ -112,6 +112,9 @@ struct Rk45Params {
   unsigned long long* next;
   int chunk;
   int refill_threshold;
+  // seeds [stat_lo, stat_hi) of this launch enter the counters (a slab's redundantly integrated
+  // halo rows do not: the counters of a sharded run then equal the single-device ones)
+  long long stat_lo, stat_hi;
 };
 
 template <int N>
@@ -218,6 +221,7 @@ __global__ void __launch_bounds__(RK_BLOCK, DLB_RK_MINBLOCKS) rk45_kernel(const 
   double y[N], f[N];
   bool fresh = true, rejected = false;
   unsigned nfev_l = 0;
+  unsigned counted = 1;  // 1 if this lane's seed enters the counters
   unsigned long long c_nfev = 0, c_acc = 0, c_rej = 0, c_fail = 0, c_seeds = 0;
 
   auto finish = [&](int st) {
@@ -229,9 +233,11 @@ __global__ void __launch_bounds__(RK_BLOCK, DLB_RK_MINBLOCKS) rk45_kernel(const 
     }
     if (P.nfev) P.nfev[idx] = nfev_l;
     if (P.status) P.status[idx] = (int8_t)st;
-    c_nfev += nfev_l;
-    c_seeds += 1;
-    if (st) c_fail += 1;
+    if (counted) {
+      c_nfev += nfev_l;
+      c_seeds += 1;
+      if (st) c_fail += 1;
+    }
     active = false;
   };
 
@@ -259,6 +265,7 @@ __global__ void __launch_bounds__(RK_BLOCK, DLB_RK_MINBLOCKS) rk45_kernel(const 
         if (!active && rank < avail) {
           // ---- start a trajectory: rk.py:86-104 (RungeKutta.__init__) ----
           idx = chunk_next + rank;
+          counted = (idx >= P.stat_lo && idx < P.stat_hi) ? 1u : 0u;
           if (GRID) {
             const long long row = idx / P.xdim;
             const long long col = idx - row * P.xdim;
@@ -387,12 +394,12 @@ __global__ void __launch_bounds__(RK_BLOCK, DLB_RK_MINBLOCKS) rk45_kernel(const 
             f[i] = K[5][i];
           }
           fresh = true;
-          c_acc += 1;
+          c_acc += counted;
           if (dir * (t - tf) >= 0) finish(0);  // base.py:207-208
         } else {
           h_abs *= dm::max_sel(pw, 0.2);
           rejected = true;
-          c_rej += 1;
+          c_rej += counted;
         }
       }
     }
@@ -497,9 +504,13 @@ int flowmap_launch(int flow_id, const double* h_params, int n_params, const doub
                    int64_t xdim, const double* d_yrows, int64_t rows, double t0, double tf,
                    double rtol, double atol, double max_step, double first_step,
                    double* d_flow_map, uint32_t* d_nfev, int8_t* d_status, uint64_t* d_counters,
-                   void* d_workspace, cudaStream_t stream) {
+                   void* d_workspace, cudaStream_t stream, int64_t stat_row0 = 0,
+                   int64_t stat_rows = -1) {
   Rk45Params P;
   memset(&P, 0, sizeof(P));
+  if (stat_rows < 0) stat_rows = rows;
+  P.stat_lo = stat_row0 * xdim;
+  P.stat_hi = (stat_row0 + stat_rows) * xdim;
   int rc = fill_common(P, flow_id, h_params, n_params, t0, tf, rtol, max_step, first_step);
   if (rc) return rc;
   P.atol[0] = P.atol[1] = P.atol[2] = atol;
@@ -583,7 +594,12 @@ extern "C" int dlb_flowmap_rk45_resident(int flow_id, const double* h_params, in
                                          double rtol, double atol, double max_step,
                                          double first_step, double* d_flow_map, uint32_t* d_nfev,
                                          int8_t* d_status, uint64_t* d_counters,
+                                         int64_t stat_row0, int64_t stat_rows,
                                          void* d_workspace, size_t workspace_bytes, void* stream_) {
+  if (stat_row0 < row0 || stat_rows < 0 || stat_row0 + stat_rows > row0 + rows) {
+    dlb_set_error("dlb_flowmap_rk45_resident: counted rows outside [row0, row0 + rows)");
+    return DLB_ERR_ARG;
+  }
   int rc = flowmap_check("dlb_flowmap_rk45_resident", flow_id, d_x, d_y, d_flow_map, d_counters,
                          d_workspace, xdim, rows, row0, atol);
   if (rc) return rc;
@@ -593,7 +609,7 @@ extern "C" int dlb_flowmap_rk45_resident(int flow_id, const double* h_params, in
   }
   return flowmap_launch(flow_id, h_params, n_params, d_x, xdim, d_y + row0, rows, t0, tf, rtol,
                         atol, max_step, first_step, d_flow_map, d_nfev, d_status, d_counters,
-                        d_workspace, (cudaStream_t)stream_);
+                        d_workspace, (cudaStream_t)stream_, stat_row0 - row0, stat_rows);
 }
 
 extern "C" int dlb_rk45_endpoints(int flow_id, const double* h_params, int n_params, int n_dim,
@@ -632,6 +648,8 @@ extern "C" int dlb_rk45_endpoints(int flow_id, const double* h_params, int n_par
   if (m == 0) return DLB_OK;
   P.seeds = d_seeds;
   P.total = m;
+  P.stat_lo = 0;
+  P.stat_hi = m;
   P.xdim = 1;
   P.out = d_out;
   P.nfev = d_nfev;

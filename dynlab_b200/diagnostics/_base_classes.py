@@ -273,14 +273,14 @@ class LagrangianDiagnostic2D(Diagnostic2D, ABC):
                     max_step=kw["max_step"], first_step=first or 0.0)
 
     def _integrate_rows(self, plan, row0, rows, out, counters=None, eng=None, y=None, nfev=None,
-                        ws_slot=None, coords=None):
+                        ws_slot=None, coords=None, stat_rows=None):
         """Enqueue K1 for rows [row0, row0 + rows) of the grid into ``out`` ([rows, xdim, 2])
         on ``eng``'s device (default: the current one)."""
         eng = eng or Engine.get()
         return eng.flow_map(plan["fid"], plan["params"], self._xf, self._yf if y is None else y,
                             row0, rows, plan["t0"], plan["tf"], plan["rtol"], plan["atol"],
                             plan["max_step"], plan["first_step"], out=out, counters=counters,
-                            nfev=nfev, ws_slot=ws_slot, coords=coords)
+                            nfev=nfev, ws_slot=ws_slot, coords=coords, stat_rows=stat_rows)
 
     # -- cost-weighted row slabs ------------------------------------------------------------
     _row_cost_cache: dict = {}
@@ -339,7 +339,8 @@ class LagrangianDiagnostic2D(Diagnostic2D, ABC):
             # integrate the (at most two) halo rows here as well: 2 / rows extra seeds, no
             # neighbour exchange and no waiting for a slower neighbour before the stencil; the
             # per-seed integration is deterministic, so the rows equal the neighbours' bit for bit
-            self._integrate_rows(plan, slab.lo, slab.nloc, local[:slab.nloc])
+            self._integrate_rows(plan, slab.lo, slab.nloc, local[:slab.nloc],
+                                 stat_rows=(slab.row0, slab.rows))
         elif slab.rows:
             own = local[slab.halo_lo:slab.halo_lo + slab.rows]
             self._integrate_rows(plan, slab.row0, slab.rows, own)

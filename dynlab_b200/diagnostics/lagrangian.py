@@ -350,7 +350,9 @@ class FTLE(LagrangianDiagnostic2D):
                     self._integrate_rows(plan, r0, r1 - r0, run["fm"][r0 - lo:r1 - lo],
                                          counters=run["counters"][c], eng=m.engine,
                                          ws_slot=(c % 2) if overlap else None,
-                                         coords=run["coords"])
+                                         coords=run["coords"],
+                                         stat_rows=(max(r0, s.row0),
+                                                    max(0, min(r1, s.row0 + s.rows) - max(r0, s.row0))))
                     if overlap:
                         ev = torch.cuda.Event()
                         ev.record(k1s)

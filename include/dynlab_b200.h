@@ -131,12 +131,15 @@ int dlb_flowmap_rk45(int flow_id, const double* h_params, int n_params,
  * least row0+rows]): nothing is uploaded, so a launch is two 64-byte memsets and the kernel.
  * Chunked / multi-GPU pipelines call this once per row chunk; an upload per launch would queue
  * behind the peer copies on the copy engines.  The workspace only holds the 256-byte work
- * counter here. */
+ * counter here.  Only the seeds of rows [stat_row0, stat_row0 + stat_rows) (a sub-range of the
+ * integrated rows; pass row0, rows for all) enter d_counters: a slab that integrates its halo
+ * rows redundantly reports the same totals as a single-device run. */
 int dlb_flowmap_rk45_resident(int flow_id, const double* h_params, int n_params,
                               const double* d_x, int64_t xdim, const double* d_y, int64_t row0,
                               int64_t rows, double t0, double tf, double rtol, double atol,
                               double max_step, double first_step, double* d_flow_map,
                               uint32_t* d_nfev, int8_t* d_status, uint64_t* d_counters,
+                              int64_t stat_row0, int64_t stat_rows,
                               void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* K1 (generic) — endpoints of m seeds of dimension n_dim (2 or 3; must match the flow).

@@ -26,8 +26,11 @@ def dl():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import dynlab_b200
-    from dynlab_b200 import diagnostics, flows, utils  # noqa: F401
+    from dynlab_b200 import diagnostics, flows, peer, utils  # noqa: F401
 
+    # the tests below talk to ONE device unless they say otherwise (a plain process on a
+    # multi-GPU box would shard every large grid by itself: test_auto_multi_device_default)
+    peer.set_devices(None)
     return dynlab_b200
 
 
@@ -1131,7 +1134,36 @@ def test_single_process_group_matches_single_device(dl):
         f = np.ma.getdata(d.compute(x, y, fl.double_gyre, t, **kw))
         assert np.array_equal(f, f1)
     finally:
-        peer.set_devices("auto")
+        peer.set_devices(None)
         sharding.set_halo_mode("redundant")
+
+
+def test_auto_multi_device_default(dl):
+    """Library default in a plain process on a multi-GPU box: a grid of >= 4 M nodes is sharded
+    over every visible device without the caller doing anything, with the single-device field,
+    flow map and integrator counters (redundant halo rows are not counted)."""
+    from dynlab_b200 import peer
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    D, fl = dl.diagnostics, dl.flows
+    x, y = np.linspace(0, 2, 2048), np.linspace(0, 1, 2051)
+    kw = dict(edge_order=2, rtol=1e-6, atol=1e-6)
+    try:
+        peer.set_devices(None)
+        a = D.FTLE()
+        fa = np.ma.getdata(a.compute(x, y, fl.double_gyre, (1.5, 0), **kw)).copy()
+        fma = a.flow_map.copy()
+        peer.set_devices("auto")
+        assert peer.current_group(len(x) * len(y)).size == torch.cuda.device_count()
+        assert peer.current_group(1000) is None  # small grids stay on one device
+        b = D.FTLE()
+        fb = np.ma.getdata(b.compute(x, y, fl.double_gyre, (1.5, 0), **kw))
+        assert np.array_equal(fa, fb) and np.array_equal(b.flow_map, fma)
+        assert b.stats == a.stats and b.stats["seeds"] == len(x) * len(y)
+        c = D.FTLE().compute_device(x, y, fl.double_gyre, (1.5, 0), **kw)
+        assert np.array_equal(c.cpu().numpy(), fa)
+    finally:
+        peer.set_devices(None)
 
 

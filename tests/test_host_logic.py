@@ -90,8 +90,11 @@ def test_peer_abi_argument_errors_without_gpu():
     assert rc == nat.DLB_ERR_ARG
     p = nat.darray([0.1, 0.2])
     rc = lib.dlb_flowmap_rk45_resident(0, p, 2, 8, 4, 8, 0, 4, 0.0, 1.0, 1e-6, 1e-6, np.inf, 0.0, 8,
-                                       None, None, 8, 8, 1 << 20, None)
+                                       None, None, 8, 0, 4, 8, 1 << 20, None)
     assert rc == nat.DLB_ERR_ARG and b"parameter count" in lib.dlb_last_error()
+    rc = lib.dlb_flowmap_rk45_resident(0, p, 2, 8, 4, 8, 2, 4, 0.0, 1.0, 1e-6, 1e-6, np.inf, 0.0, 8,
+                                       None, None, 8, 1, 4, 8, 1 << 20, None)  # counted rows 1..4 of 2..5
+    assert rc == nat.DLB_ERR_ARG and b"counted rows" in lib.dlb_last_error()
 
 
 # ------------------------------------------------------------------ flows / resolver / utils
