@@ -220,8 +220,7 @@ __global__ void __launch_bounds__(RK_BLOCK, DLB_RK_MINBLOCKS) rk45_kernel(const 
   double t = 0.0, h_abs = 0.0;
   double y[N], f[N];
   bool fresh = true, rejected = false;
-  unsigned nfev_l = 0;
-  unsigned counted = 1;  // 1 if this lane's seed enters the counters
+  unsigned nfev_l = 0, rej_l = 0;  // per trajectory: RHS evaluations, rejected attempts
   unsigned long long c_nfev = 0, c_acc = 0, c_rej = 0, c_fail = 0, c_seeds = 0;
 
   auto finish = [&](int st) {
@@ -233,8 +232,12 @@ __global__ void __launch_bounds__(RK_BLOCK, DLB_RK_MINBLOCKS) rk45_kernel(const 
     }
     if (P.nfev) P.nfev[idx] = nfev_l;
     if (P.status) P.status[idx] = (int8_t)st;
-    if (counted) {
+    if (idx >= P.stat_lo && idx < P.stat_hi) {  // (a slab's redundant halo rows are not counted)
+      // attempts = (nfev - 1) / 6 whether the start-up took one RHS evaluation or two
+      const unsigned attempts = (nfev_l - 1u) / 6u;
       c_nfev += nfev_l;
+      c_acc += attempts - rej_l;
+      c_rej += rej_l;
       c_seeds += 1;
       if (st) c_fail += 1;
     }
@@ -265,7 +268,6 @@ __global__ void __launch_bounds__(RK_BLOCK, DLB_RK_MINBLOCKS) rk45_kernel(const 
         if (!active && rank < avail) {
           // ---- start a trajectory: rk.py:86-104 (RungeKutta.__init__) ----
           idx = chunk_next + rank;
-          counted = (idx >= P.stat_lo && idx < P.stat_hi) ? 1u : 0u;
           if (GRID) {
             const long long row = idx / P.xdim;
             const long long col = idx - row * P.xdim;
@@ -278,6 +280,7 @@ __global__ void __launch_bounds__(RK_BLOCK, DLB_RK_MINBLOCKS) rk45_kernel(const 
           t = P.t0;
           flow_rhs<ID>(P.fc, t, y, f);  // rk.py:94
           nfev_l = 1;
+          rej_l = 0;
           fresh = true;
           rejected = false;
           active = true;
@@ -394,12 +397,12 @@ __global__ void __launch_bounds__(RK_BLOCK, DLB_RK_MINBLOCKS) rk45_kernel(const 
             f[i] = K[5][i];
           }
           fresh = true;
-          c_acc += counted;
+          // (accepted steps are derived from nfev when the trajectory ends: nothing to count here)
           if (dir * (t - tf) >= 0) finish(0);  // base.py:207-208
         } else {
           h_abs *= dm::max_sel(pw, 0.2);
           rejected = true;
-          c_rej += counted;
+          rej_l += 1;
         }
       }
     }
