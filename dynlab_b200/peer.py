@@ -51,6 +51,10 @@ class Member:
         return self.engine.device
 
 
+class PeerTransportUnavailable(RuntimeError):
+    """The GPUs of this job cannot map each other's memory (CUDA IPC / peer access refused)."""
+
+
 class _Raw:
     """Lets torch alias a raw device allocation (``torch.as_tensor`` reads this protocol)."""
 
@@ -115,17 +119,29 @@ class Group:
                 nat.check(nat.lib.dlb_ipc_export(own_ptr[m.rank], handle))
                 handles = [None] * self.size
                 dist.all_gather_object(handles, handle.raw)
-                row = []
+                row, problem = [], None
                 for j in range(self.size):
                     if j == m.rank:
                         row.append(own_ptr[m.rank])
-                    else:
-                        p = C.c_void_p()
-                        nat.check(nat.lib.dlb_ipc_open(handles[j], C.byref(p)))
-                        row.append(p.value)
-                        closers.append(p.value)
+                        continue
+                    p = C.c_void_p()
+                    rc = nat.lib.dlb_ipc_open(handles[j], C.byref(p))
+                    if rc != nat.DLB_OK:
+                        problem = (nat.lib.dlb_last_error() or b"").decode()
+                        break
+                    row.append(p.value)
+                    closers.append(p.value)
             addr = {m.rank: row}
-            dist.barrier()  # nobody pushes into a block its owner has not finished zeroing
+            # doubles as the barrier "nobody pushes into a block its owner has not finished
+            # zeroing"; every rank learns whether every mapping worked
+            problems = [None] * self.size
+            dist.all_gather_object(problems, problem)
+            if any(problems):
+                for q in closers:
+                    nat.lib.dlb_ipc_close(q)
+                dist.barrier()  # every importer has unmapped before an owner frees
+                nat.lib.dlb_peer_free(own_ptr[m.rank])
+                raise PeerTransportUnavailable(next(q for q in problems if q))
         else:
             row = [own_ptr[r] for r in range(self.size)]
             addr = {m.rank: row for m in self.local}
@@ -319,7 +335,16 @@ def current_group(n_seeds=None):
         key = ("mp", rank, size, torch.cuda.current_device())
         g = _groups.get(key)
         if g is None:
-            g = _groups[key] = Group(size, [Member(rank, Engine.get())], True)
+            try:
+                g = _groups[key] = Group(size, [Member(rank, Engine.get())], True)
+            except PeerTransportUnavailable as exc:
+                # decided collectively (Group.symmetric): every rank lands here together
+                import warnings
+
+                warnings.warn(f"dynlab_b200: peer-memory transport unavailable ({exc}); the ranks "
+                              "fall back to NCCL for halo and gather", RuntimeWarning)
+                sharding.set_transport("nccl")
+                return None
         return g
     devs = _single_process_devices(n_seeds)
     if devs is None:

@@ -356,10 +356,12 @@ def gather_slab(part, slab: "Slab", ydim: int, tail, dtype, device) -> torch.Ten
     (``"nccl"`` transport, CPU tensors under gloo): padded all-gather through torch.distributed."""
     rank, size = world()
     tail = tuple(int(v) for v in tail)
+    G = None
     if torch.device(device).type == "cuda" and _transport == "peer":
         from . import peer
 
-        G = peer.current_group()
+        G = peer.current_group()  # None if the GPUs cannot map each other's memory (-> NCCL)
+    if G is not None:
         (m,) = G.local
         gen = G.next_generation()
         item = torch.empty((), dtype=dtype).element_size()
