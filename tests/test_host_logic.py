@@ -260,6 +260,16 @@ def _shard_worker(rank, size, port, ydim, xdim, edge_order, out_dir):
             out[:slab.rows] = torch.from_numpy(loc[slab.halo_lo:slab.halo_lo + slab.rows])
         got = sharding.gather_rows(out, ydim, size).numpy()
         assert got.shape == full.shape
+        # gather_slab: the same through the entry the diagnostics use (CPU tensors -> the
+        # torch.distributed branch; on CUDA the peer-memory branch, checked by the gpu tests)
+        part = out[:slab.rows] if slab.rows else None
+        got2 = sharding.gather_slab(part, slab, ydim, (xdim,), torch.float64, "cpu").numpy()
+        assert np.array_equal(got2, got)
+        m8 = torch.full((max(slab.rows, 1), xdim), rank + 1, dtype=torch.uint8)
+        gm = sharding.gather_slab(m8 if slab.rows else None, slab, ydim, (xdim,), torch.uint8, "cpu")
+        for r in range(size):
+            sr = sharding.partition(ydim, size, r)
+            assert (gm[sr.row0:sr.row0 + sr.rows] == r + 1).all()
         # rows next to an interior cut used a one-sided oracle formula locally only if the slab
         # had no halo there — with halos every own row matches the unsharded result
         np.testing.assert_allclose(got, full, rtol=1e-12, atol=1e-12)
