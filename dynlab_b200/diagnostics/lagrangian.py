@@ -98,6 +98,14 @@ def member_schedule(slab, ydim, edge_order, exchange, chunks, last_fraction):
                              last_fraction), []
 
 
+def counted_rows(r0, r1, slab):
+    """(first row, number of rows) of the K1 chunk [r0, r1) whose seeds enter the integrator
+    counters: the chunk's intersection with the member's OWN rows (redundantly integrated halo
+    rows are computed but not counted, so a sharded run reports the single-device totals)."""
+    a, b = max(r0, slab.row0), min(r1, slab.row0 + slab.rows)
+    return (a, b - a) if b > a else (r0, 0)
+
+
 class FTLE(LagrangianDiagnostic2D):
     """Finite-time Lyapunov exponent field of a 2-D flow (R:lagrangian.py:9-78)."""
 
@@ -351,8 +359,7 @@ class FTLE(LagrangianDiagnostic2D):
                                          counters=run["counters"][c], eng=m.engine,
                                          ws_slot=(c % 2) if overlap else None,
                                          coords=run["coords"],
-                                         stat_rows=(max(r0, s.row0),
-                                                    max(0, min(r1, s.row0 + s.rows) - max(r0, s.row0))))
+                                         stat_rows=counted_rows(r0, r1, s))
                     if overlap:
                         ev = torch.cuda.Event()
                         ev.record(k1s)

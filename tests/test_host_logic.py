@@ -539,7 +539,7 @@ def test_member_schedule_invariants():
     output row is produced exactly once, in order, and only from rows that exist locally at that
     moment (integrated chunks; after the exchange also the halo slots)."""
     from dynlab_b200 import sharding as sh
-    from dynlab_b200.diagnostics.lagrangian import member_schedule
+    from dynlab_b200.diagnostics.lagrangian import counted_rows, member_schedule
 
     def need(a, b, ydim, eo):
         lo, hi = max(a - 1, 0), min(b, ydim - 1)
@@ -579,6 +579,14 @@ def test_member_schedule_invariants():
                                 produced.append((a, b))
                             rows = sorted(r for a, b in produced for r in range(a, b))
                             assert rows == list(range(s.row0, s.row0 + s.rows)), (ydim, size, rank, eo, exchange)
+                            # integrator counters: every own row counted exactly once, halo
+                            # rows never, and the counted range lies inside its chunk
+                            counted = []
+                            for r0, r1, _, _ in steps:
+                                c0, cn = counted_rows(r0, r1, s)
+                                assert r0 <= c0 and c0 + cn <= r1 and cn >= 0
+                                counted += list(range(c0, c0 + cn))
+                            assert counted == list(range(s.row0, s.row0 + s.rows))
 
 
 def test_bench_reference_arm_json_contract():
