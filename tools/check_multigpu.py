@@ -83,13 +83,12 @@ for (nx, ny, eo, t) in grids:
                     f = np.ma.getdata(d.compute(x, y, double_gyre, t, **kw)).copy()
                     results[f"{tag}/host:{host}"] = np.array_equal(f, f_1)
                 sharding.set_host_result("shared")
-                # integrator counters: this rank's seeds; summed over ranks = the single run
-                # (redundant halo rows are extra work, so only check the exchange mode)
-                if halo == "exchange":
-                    tot = torch.tensor([d.stats["nfev"]], dtype=torch.int64,
-                                       device="cuda" if args.backend == "nccl" else "cpu")
-                    dist.all_reduce(tot)
-                    results[f"{tag}/nfev"] = int(tot.item()) == nfev_1
+                # integrator counters: this rank's seeds; summed over ranks = the single run (in
+                # both halo modes: redundantly integrated halo rows are not counted)
+                tot = torch.tensor([d.stats["nfev"], d.stats["seeds"]], dtype=torch.int64,
+                                   device="cuda" if args.backend == "nccl" else "cpu")
+                dist.all_reduce(tot)
+                results[f"{tag}/nfev"] = tot.tolist() == [nfev_1, nx * ny]
                 if not (args.full and nx == 8192 and (tr, halo) != ("peer", "exchange")):
                     results[f"{tag}/flow_map"] = np.array_equal(d.flow_map, fm_1)
                 for rep in range(2):  # twice: rotating result buffers
