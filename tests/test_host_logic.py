@@ -611,3 +611,81 @@ def test_bench_reference_arm_json_contract():
     e2e = line["e2e"]
     assert e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
     assert e2e["unit"] == line["unit"] and abs(e2e["value"] - line["value"]) <= 1e-9 * line["value"]
+
+
+# ------------------------------------------------------------------ constants of the CUDA sources
+def _c_double_table(path, name):
+    """Values of `__constant__ double NAME[...] = { ... };` in a CUDA source, evaluated like C
+    (hex floats, integer-looking literals with a decimal point, a / b quotients)."""
+    src = open(path).read()
+    body = re.search(name + r"\[\d+\]\s*=\s*\{(.*?)\};", src, flags=re.S).group(1)
+    body = re.sub(r"//[^\n]*", "", body)
+    out = []
+    for tok in body.split(","):
+        tok = tok.strip()
+        if not tok:
+            continue
+        if "0x" in tok:
+            out.append(float.fromhex(tok))
+        elif "/" in tok:
+            a, b = tok.split("/")
+            out.append(float(a) / float(b))
+        else:
+            out.append(float(tok))
+    return out
+
+
+def test_rk45_tableau_in_cuda_source_is_scipys():
+    """csrc/rk45.cu states the Dormand-Prince tableau as literals: it must be scipy's RK45
+    (scipy/integrate/_ivp/rk.py:538-552), value for value."""
+    from scipy.integrate._ivp.rk import RK45
+
+    t = _c_double_table(os.path.join(ROOT, "dynlab_b200", "csrc", "rk45.cu"), "RKT")
+    A, B, E, Cn = RK45.A, RK45.B, RK45.E, RK45.C
+    a_flat = [A[i][j] for i in range(1, 6) for j in range(i)]
+    assert t[:15] == a_flat
+    assert t[15:20] == [B[0], B[2], B[3], B[4], B[5]] and B[1] == 0
+    assert t[20:26] == [E[0], E[2], E[3], E[4], E[5], E[6]] and E[1] == 0
+    assert t[26:30] == list(Cn[1:5]) and Cn[5] == 1.0
+
+
+def test_device_trig_constants_and_halfturn_sine_model():
+    """csrc/dmath.cuh: pi/2 and pi splits, 2/pi, 1/pi, and the Taylor coefficients of the
+    half-turn sine; a float64 model of that sine (the kernel's operations, FMAs emulated in
+    long double) stays within 2 ulp of sin on the stage-time arguments of an integration."""
+    import math
+
+    K = _c_double_table(os.path.join(ROOT, "dynlab_b200", "csrc", "dmath.cuh"), "DM_K")
+    ld = np.longdouble
+    assert K[0] == 2 / math.pi and K[30] == 1 / math.pi and K[18] == math.pi
+    assert K[1] == math.pi / 2 and K[4] == 1.5 * 2.0 ** 52
+    # pi/2 = P1 + P2 + P3 and pi = K18 + K19: the splits are the rounding residues of the previous terms
+    mp = pytest.importorskip("mpmath")
+    mp.mp.prec = 400
+    assert K[2] == float(mp.pi / 2 - mp.mpf(K[1]))
+    assert K[3] == float(mp.pi / 2 - mp.mpf(K[1]) - mp.mpf(K[2]))
+    assert K[19] == 2 * K[2]
+    for i in range(10):
+        assert K[20 + i] == (-1) ** (i + 1) / math.factorial(2 * i + 3)
+
+    def fma(a, b, c):
+        return (ld(a) * ld(b) + ld(c)).astype(np.float64)
+
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-7, 7, 50000), rng.uniform(-1e-3, 1e-3, 5000),
+                        math.pi * np.arange(-2, 3) + rng.uniform(-1e-9, 1e-9, 5)])
+    t = fma(x, K[30], K[4])
+    q = t.view(np.int64) & 1
+    fq = t - K[4]
+    r = fma(-fq, K[19], fma(-fq, K[18], x))
+    z = r * r
+    p = fma(np.full_like(x, K[29]), z, K[28])
+    for k in range(27, 19, -1):
+        p = fma(p, z, K[k])
+    s = np.where(q == 1, -1.0, 1.0) * fma(r * z, p, r)
+    ref = np.sin(ld(x))
+    ulp = np.abs(ld(s) - ref) / np.spacing(np.abs(ref.astype(np.float64)))
+    # (the long-double stand-in for the FMA keeps 11 fraction bits next to the magic constant, so
+    # a quotient within 2.4e-4 of a half-integer may round the other way here: |r| <= pi/2 + 1e-3)
+    assert np.abs(r).max() <= math.pi / 2 + 1e-3
+    assert float(ulp.max()) < 2.0 and float((ulp > 1).mean()) < 0.02
