@@ -6,21 +6,28 @@ edge_order=2, rtol=atol=1e-8), one process per GPU.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-A step = one pass of the hot path over the whole seed grid:
-K1 (RK45 flow map of this rank's row slab) -> 1-row halo exchange -> K2 (fused stencil/eigen)
--> gather of the FTLE rows.
+A step = one pass of the hot path over the whole seed grid with the library's defaults:
+K1 (RK45 flow map of this rank's row slab, cut by integrator work, halo rows integrated locally)
+-> K2 (fused stencil / eigen / log) -> the FTLE rows to every rank (peer-memory push behind K1,
+the last rows by K2's own epilogue; csrc/peer.cu).
   value : seeds/s with everything resident in HBM (CUDA events, max over ranks).
   e2e   : seeds/s through the public API FTLE().compute(x, y, f, t, ...) with host numpy
-          coordinates in and the host FTLE field out (pinned D2H inside the timed region).
+          coordinates in and the host FTLE field out on every rank (D2H inside the timed region).
+  result_check  : sha256 of the value / e2e fields (all ranks compared) and the C-oracle error
+                  of the flow map on the every-64th sample - the same at every N.
   roofline      : K1, FP64-bound: algorithmic FLOP (SURVEY §8d model, from the kernel's exact
-                  attempt counter) / K1's mean launch duration, against the DFMA peak measured
+                  attempt counter) / K1's launch time per step, against the DFMA peak measured
                   in this run (MEASURED_PEAKS.json has no FP64 figure).
-  roofline_hbm  : K2, HBM-bound: 24 B/point / launch duration against MEASURED_PEAKS hbm_gbs.
-  cpu_baseline  : the plain-C oracle port of the same algorithm on all host cores, bounded
-                  strided sample of the same grid (rank 0, N=1 only).
---impl reference times the reference's own CPU implementation of the path (faithful Python
-port: scipy LSODA through the seed loop with a process pool over all cores + np.gradient +
-np.linalg.eig loop, oracle/py_oracle.py) on a bounded strided sample.
+  roofline_hbm  : K2: 24 B/point / launch duration against MEASURED_PEAKS hbm_gbs.
+  cpu_baseline  : N = 1: the UNMODIFIED reference (oracle/_ref) FTLE(num_threads=cores) with
+                  its default LSODA integrator on a strided sample, in a fresh interpreter;
+                  beside it the reference with a scipy RK45 integrator and the plain-C port.
+  configs       : driver-timed lines for BASELINE configs[1], [3], [4] (N = 1; the sweep at all N).
+  single_process: N > 1: rank 0 alone drives all N GPUs in one process (no torch.distributed).
+  nccl_transport_ms_per_step: N > 1: the same step with NCCL carrying halo + gather (A/B).
+--impl reference times the reference's own CPU implementation of the path: the unmodified
+package from oracle/_ref (kind "reference"; oracle/py_oracle.py, kind "port", only if the copy
+is absent) on a bounded strided sample, all host cores.
 """
 from __future__ import annotations
 
