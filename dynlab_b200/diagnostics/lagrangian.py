@@ -467,6 +467,8 @@ class FTLE(LagrangianDiagnostic2D):
                     cost = self._row_costs(plan, G.local[0].engine)
                     if cost is not None:
                         b = sharding.weighted_bounds(self.ydim, G.size, cost)
+            if len(self._row_cost_cache) > 32:  # keys carry the coordinate bytes: keep it small
+                self._row_cost_cache.clear()
             self._row_cost_cache[key] = b
         return b
 
