@@ -450,7 +450,9 @@ class FTLE(LagrangianDiagnostic2D):
         key = ("bounds", G.size, bool(self.weighted_slabs), plan["fid"], tuple(plan["params"]),
                plan["t0"], plan["tf"], plan["rtol"], plan["atol"], self._xf.tobytes(),
                self._yf.tobytes())
-        b = self._row_cost_cache.get(key)
+        # its own dict: under torchrun every rank must hit or miss together (a miss is a
+        # collective), and only rank 0 also stores pilot results in _row_cost_cache
+        b = self._bounds_cache.get(key)
         if b is None:
             b = sharding.uniform_bounds(self.ydim, G.size)
             if self.weighted_slabs and G.size > 1:
@@ -467,10 +469,12 @@ class FTLE(LagrangianDiagnostic2D):
                     cost = self._row_costs(plan, G.local[0].engine)
                     if cost is not None:
                         b = sharding.weighted_bounds(self.ydim, G.size, cost)
-            if len(self._row_cost_cache) > 32:  # keys carry the coordinate bytes: keep it small
-                self._row_cost_cache.clear()
-            self._row_cost_cache[key] = b
+            if len(self._bounds_cache) > 32:  # keys carry the coordinate bytes: keep it small
+                self._bounds_cache.clear()
+            self._bounds_cache[key] = b
         return b
+
+    _bounds_cache: dict = {}
 
     weighted_slabs = True  # cut the slabs by integrator work instead of by rows (large grids)
     # K1 chunks on alternating streams (chunk c+1 fills the SMs as chunk c drains), K2 on its own

@@ -142,7 +142,7 @@ for (nx, ny, eo, t) in grids:
     ok = ok and not bad
     say(f"grid {nx}x{ny} eo={eo} t={t} world={world}: {len(results)} checks, "
         f"{'all bit-identical to the single-GPU result' if not bad else 'MISMATCH: ' + ', '.join(bad)}"
-        f" [bounds {FTLE._row_cost_cache and 'cached'}]" + extra)
+        f" [{len(FTLE._bounds_cache)} slab cuts cached]" + extra)
 flag = torch.tensor([1 if ok else 0], device="cuda" if args.backend == "nccl" else "cpu")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
